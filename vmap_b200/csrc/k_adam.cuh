@@ -1,0 +1,86 @@
+// K2: fused stacked AdamW over the packed [n_obj][stride] fp32 param block.
+// Restates torch.optim.AdamW.step() as the reference drives it (train.py:67,325-326;
+// groups added by utils.py:33): decoupled decay on every tensor, default betas/eps,
+// one shared step counter (all stacked tensors are always stepped together), followed by
+// zero_grad.  Optionally refreshes the fp16 tensor-core weight image consumed by the
+// UMMA step kernel, so K1 can stage an object's weights with one bulk copy.
+#pragma once
+#include "common.cuh"
+
+struct AdamParams {
+  long long n;                // B * stride
+  int stride, P;              // row pitch, live floats per row
+  int B;
+  float* p; float* g; float* m; float* v;
+  __half* image; const int* img_index; int img_halves;   // per-object image size in halves
+  const float* loss_terms; int* status;
+  float lr_wd;                // 1 - lr*wd
+  float one_m_b1, b2, one_m_b2;
+  float step_size;            // lr / (1 - b1^t)
+  float bc2_sqrt;             // sqrt(1 - b2^t)
+  float eps;
+  int zero_grads;
+};
+
+__global__ void __launch_bounds__(256) k_adamw(AdamParams a) {
+  __shared__ int s_skip;
+  if (threadIdx.x == 0) s_skip = 0;
+  __syncthreads();
+  if (a.loss_terms) {       // render_rays.py:88-90: the reference aborts before the update
+    int bad = 0;
+    for (int i = threadIdx.x; i < a.B * 4; i += blockDim.x) {
+      const float l = a.loss_terms[i];
+      if ((i & 3) != 3 && l > 100000.f) bad |= 1;
+      if (!(l == l) || fabsf(l) > 3.0e38f) bad |= 2;
+    }
+    if (bad) atomicOr(&s_skip, bad);
+    __syncthreads();
+    if (s_skip) {
+      if (blockIdx.x == 0 && threadIdx.x == 0 && a.status) atomicOr(a.status, s_skip);
+      return;
+    }
+  }
+  const long long i4 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i4 >= a.n) return;
+  float4 p = *reinterpret_cast<float4*>(a.p + i4);
+  float4 g = *reinterpret_cast<float4*>(a.g + i4);
+  float4 m = *reinterpret_cast<float4*>(a.m + i4);
+  float4 v = *reinterpret_cast<float4*>(a.v + i4);
+  float* pp = &p.x; float* gg = &g.x; float* mm = &m.x; float* vv = &v.x;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float pj = pp[j] * a.lr_wd;                                  // p.mul_(1 - lr*wd)
+    const float mj = mm[j] + (gg[j] - mm[j]) * a.one_m_b1;       // exp_avg.lerp_(g, 1-b1)
+    const float vj = vv[j] * a.b2 + (a.one_m_b2 * gg[j]) * gg[j];// exp_avg_sq.mul_(b2).addcmul_(g,g,1-b2)
+    const float denom = sqrtf(vj) / a.bc2_sqrt + a.eps;
+    pj = pj - a.step_size * (mj / denom);                        // p.addcdiv_(m, denom, -step_size)
+    pp[j] = pj; mm[j] = mj; vv[j] = vj;
+  }
+  *reinterpret_cast<float4*>(a.p + i4) = p;
+  *reinterpret_cast<float4*>(a.m + i4) = m;
+  *reinterpret_cast<float4*>(a.v + i4) = v;
+  if (a.zero_grads) *reinterpret_cast<float4*>(a.g + i4) = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (a.image) {
+    const int b = (int)(i4 / a.stride);
+    const int e = (int)(i4 - (long long)b * a.stride);
+    __half* img = a.image + (size_t)b * a.img_halves;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (e + j < a.P) {
+        const int t = a.img_index[e + j];
+        if (t >= 0) img[t] = __float2half_rn(pp[j]);
+      }
+    }
+  }
+}
+
+// fp32 master weights -> fp16 image (init / checkpoint load / re-stack)
+__global__ void __launch_bounds__(256) k_build_image(int B, int stride, int P, const float* p,
+                                                      __half* image, const int* img_index, int img_halves) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)B * stride) return;
+  const int b = (int)(i / stride), e = (int)(i - (long long)b * stride);
+  if (e >= P) return;
+  const int t = img_index[e];
+  if (t >= 0) image[(size_t)b * img_halves + t] = __float2half_rn(p[i]);
+}

@@ -1,0 +1,194 @@
+// K3: batched depth-guided ray sampler -- one launch for every object of the frame.
+// Restates sceneObject.get_training_samples + sample_3d_points + stratified_bins +
+// normal_bins_sampling + origin_dirs_W (vmap.py:319-364, 366-459, 45-72, 75-87, 31-41)
+// per ray instead of per compacted group, and folds in the stack + /255 of
+// train.py:255-260.  No host syncs: the data-dependent max_bound (vmap.py:397) is a
+// block reduction (one CTA per object), the group branches are per-ray selects.
+//
+// Index / bin arithmetic uses explicit round-to-nearest mul/add (no FMA contraction) so
+// that with injected randoms the integer outputs and z are bit-identical to torch's
+// separate fp32 ops.  Randoms come from Philox4x32-10 counters keyed by
+// (seed, object, stream, ray) unless injected.
+#pragma once
+#include "common.cuh"
+
+struct SampleParams {
+  int B, n_frames, n_pix, n1, n2, W, Hh;
+  float min_bound, eps, oeps;
+  const unsigned char* const* rgbs;
+  const float* const* depths;
+  const float* const* t_wc;
+  const float* const* bbox;
+  const int* n_kf;
+  const int* latest;
+  const float* rays_dir;
+  const float* lim;           // [3][33]
+  unsigned long long seed, offset;
+  const long long* inj_kf; const float* inj_u_w; const float* inj_u_h; const float* inj_u_z; const float* inj_nrm;
+  float* pcs; float* z; float* gt_depth; float* gt_colour; unsigned char* rgb_u8;
+  unsigned char* sem; unsigned char* mask;
+};
+
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                              uint32_t k0, uint32_t k1, uint32_t (&out)[4]) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+__device__ __forceinline__ float u01(uint32_t x) { return (float)(x & 0xFFFFFFu) * (1.0f / 16777216.0f); }
+
+struct RayPick { int kf, iw, ih; };
+
+__device__ __forceinline__ RayPick pick_pixel(const SampleParams& a, int b, int i) {
+  const int f = i / a.n_pix;
+  const int nkf = a.n_kf[b];
+  const uint32_t k0 = (uint32_t)a.seed, k1 = (uint32_t)(a.seed >> 32);
+  RayPick r;
+  if (a.inj_kf) {
+    r.kf = (int)a.inj_kf[(size_t)b * a.n_frames + f];
+  } else if (nkf > 2 && f >= a.n_frames - 2) {                    // vmap.py:321-331
+    r.kf = a.latest[b * 2 + (f - (a.n_frames - 2))];
+  } else {
+    uint32_t o[4];
+    philox4x32_10((uint32_t)f, 0u, (uint32_t)b, (uint32_t)a.offset, k0, k1, o);
+    r.kf = min((int)(u01(o[0]) * (float)nkf), nkf - 1);
+  }
+  float uw, uh;
+  if (a.inj_u_w) {
+    uw = a.inj_u_w[(size_t)b * a.n_frames * a.n_pix + i];
+    uh = a.inj_u_h[(size_t)b * a.n_frames * a.n_pix + i];
+  } else {
+    uint32_t o[4];
+    philox4x32_10((uint32_t)i, 1u, (uint32_t)b, (uint32_t)a.offset, k0, k1, o);
+    uw = u01(o[0]); uh = u01(o[1]);
+  }
+  const float* bb = a.bbox[b] + r.kf * 4;                         // vmap.py:346-351
+  r.iw = (int)__fadd_rn(__fmul_rn(uw, __fsub_rn(bb[1], bb[0])), bb[0]);
+  r.ih = (int)__fadd_rn(__fmul_rn(uh, __fsub_rn(bb[3], bb[2])), bb[2]);
+  r.iw = min(max(r.iw, 0), a.W - 1);
+  r.ih = min(max(r.ih, 0), a.Hh - 1);
+  return r;
+}
+
+// stratified_bins (vmap.py:45-72) for one ray / one bin
+__device__ __forceinline__ float strat(float lo, float hi, const float* lim, int n, int k, float u) {
+  const float rng = __fsub_rn(hi, lo);
+  const float lower = __fadd_rn(__fmul_rn(rng, lim[k]), lo);
+  return __fadd_rn(lower, __fmul_rn(u, __fdiv_rn(rng, (float)n)));
+}
+
+__global__ void __launch_bounds__(512) k_sample(SampleParams a) {
+  const int b = blockIdx.x;
+  const int N = a.n_frames * a.n_pix;
+  const int S = a.n1 + a.n2;
+  __shared__ float s_max[16];
+  __shared__ float s_maxb;
+  const size_t pix_per_kf = (size_t)a.W * a.Hh;
+
+  // pass 1: gather pixels, write the 2-D targets, reduce max depth (vmap.py:353-354,397)
+  float mx = -3.0e38f;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    const RayPick r = pick_pixel(a, b, i);
+    const size_t pi = (size_t)r.kf * pix_per_kf + (size_t)r.iw * a.Hh + r.ih;
+    const uchar4 px = reinterpret_cast<const uchar4*>(a.rgbs[b])[pi];
+    const float d = a.depths[b][pi];
+    const size_t o = (size_t)b * N + i;
+    a.gt_depth[o] = d;
+    a.gt_colour[o * 3 + 0] = (float)px.x / 255.f;                 // train.py:257
+    a.gt_colour[o * 3 + 1] = (float)px.y / 255.f;
+    a.gt_colour[o * 3 + 2] = (float)px.z / 255.f;
+    if (a.rgb_u8) { a.rgb_u8[o * 3] = px.x; a.rgb_u8[o * 3 + 1] = px.y; a.rgb_u8[o * 3 + 2] = px.z; }
+    a.sem[o] = px.w;
+    a.mask[o] = !(d <= a.min_bound);                              // vmap.py:395,407
+    mx = fmaxf(mx, d);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0) s_max[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float m = s_max[0];
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) m = fmaxf(m, s_max[w]);
+    s_maxb = m;
+  }
+  __syncthreads();
+  const float max_bound = s_maxb;
+
+  // pass 2: per-ray sample depths and 3-D points (vmap.py:366-459)
+  const float* limS = a.lim, * lim1 = a.lim + 33, * lim2 = a.lim + 66;
+  const uint32_t k0 = (uint32_t)a.seed, k1 = (uint32_t)(a.seed >> 32);
+  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    const RayPick r = pick_pixel(a, b, i);
+    const size_t o = (size_t)b * N + i;
+    const float d = a.gt_depth[o];
+    const int state = a.sem[o];
+    const bool invalid = d <= a.min_bound;
+    const bool this_obj = (state == 1) && !invalid;
+
+    float uz[32], nz[32];
+    if (a.inj_u_z) {
+      for (int s = 0; s < S; ++s) uz[s] = a.inj_u_z[o * S + s];
+    } else {
+      for (int c = 0; c * 4 < S; ++c) {
+        uint32_t q[4];
+        philox4x32_10((uint32_t)i * 8u + c, 2u, (uint32_t)b, (uint32_t)a.offset, k0, k1, q);
+        for (int j = 0; j < 4 && c * 4 + j < S; ++j) uz[c * 4 + j] = u01(q[j]);
+      }
+    }
+    if (this_obj) {
+      if (a.inj_nrm) {
+        for (int s = 0; s < a.n2; ++s) nz[s] = a.inj_nrm[o * a.n2 + s];
+      } else {
+        const float sd = a.eps / 3.0f;                            // vmap.py:432 delta/3
+        for (int c = 0; c * 4 < a.n2; ++c) {
+          uint32_t q[4];
+          philox4x32_10((uint32_t)i * 8u + c, 3u, (uint32_t)b, (uint32_t)a.offset, k0, k1, q);
+          const float r0 = sqrtf(-2.f * logf(1.f - u01(q[0]))), r1 = sqrtf(-2.f * logf(1.f - u01(q[2])));
+          float s0, c0, s1, c1;
+          sincospif(2.f * u01(q[1]), &s0, &c0);
+          sincospif(2.f * u01(q[3]), &s1, &c1);
+          const float g[4] = {r0 * c0, r0 * s0, r1 * c1, r1 * s1};
+          for (int j = 0; j < 4 && c * 4 + j < a.n2; ++j) nz[c * 4 + j] = g[j] * sd;
+        }
+      }
+      for (int x = 1; x < a.n2; ++x) {                            // .sort() (vmap.py:81)
+        const float v = nz[x];
+        int y = x - 1;
+        while (y >= 0 && nz[y] > v) { nz[y + 1] = nz[y]; --y; }
+        nz[y + 1] = v;
+      }
+    }
+
+    const float* dc = a.rays_dir + ((size_t)r.iw * a.Hh + r.ih) * 3;   // vmap.py:357
+    const float* T = a.t_wc[b] + r.kf * 16;                            // vmap.py:360
+    const float dw0 = fmaf(T[2], dc[2], fmaf(T[1], dc[1], T[0] * dc[0]));      // vmap.py:37
+    const float dw1 = fmaf(T[6], dc[2], fmaf(T[5], dc[1], T[4] * dc[0]));
+    const float dw2 = fmaf(T[10], dc[2], fmaf(T[9], dc[1], T[8] * dc[0]));
+    const float o0 = T[3], o1 = T[7], o2 = T[11];                              // vmap.py:39
+
+    for (int s = 0; s < S; ++s) {
+      float zz;
+      if (invalid) {
+        zz = strat(a.min_bound, max_bound, limS, S, s, uz[s]);                 // vmap.py:400-404
+      } else if (s < a.n1) {
+        zz = strat(a.min_bound, __fsub_rn(d, a.eps), lim1, a.n1, s, uz[s]);    // vmap.py:413-415
+      } else if (this_obj) {
+        const float bn = fminf(fmaxf(nz[s - a.n1], -a.eps), a.eps);            // vmap.py:82
+        zz = __fadd_rn(d, bn);                                                 // vmap.py:83
+      } else {
+        zz = strat(__fsub_rn(d, a.eps), __fadd_rn(d, a.oeps), lim2, a.n2, s - a.n1, uz[s]);   // vmap.py:447-450
+      }
+      a.z[o * S + s] = zz;
+      float* pc = a.pcs + (o * S + s) * 3;                                     // vmap.py:455
+      pc[0] = __fadd_rn(o0, __fmul_rn(dw0, zz));
+      pc[1] = __fadd_rn(o1, __fmul_rn(dw1, zz));
+      pc[2] = __fadd_rn(o2, __fmul_rn(dw2, zz));
+    }
+  }
+}

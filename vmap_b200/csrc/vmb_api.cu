@@ -1,0 +1,265 @@
+// C ABI of libvmap_b200.so (see include/vmap_b200.h).  Host-side launch logic only.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cmath>
+#include <string>
+#include <vector>
+
+#include "../../include/vmap_b200.h"
+#include "common.cuh"
+#include "k_step_fp32.cuh"
+#include "k_adam.cuh"
+#include "k_sampler.cuh"
+#include "k_step_umma.cuh"
+
+struct vmb_handle {
+  int device, max_obj, H, nfreq;
+  VmbLayout L;
+  int* d_counts;          // [max_obj][4]
+  int* d_img_index;       // [P] param index -> half index inside the fp16 image (or -1)
+  int img_halves;
+  bool umma_ok;
+  std::string err;
+};
+
+static thread_local std::string g_err;
+
+static int fail(vmb_handle* h, int code, const std::string& msg) {
+  if (h) h->err = msg;
+  g_err = msg;
+  return code;
+}
+#define CUDA_TRY(h, expr)                                                                  \
+  do {                                                                                     \
+    cudaError_t e_ = (expr);                                                               \
+    if (e_ != cudaSuccess)                                                                 \
+      return fail(h, VMB_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));      \
+  } while (0)
+
+template <int H, int TP>
+static int launch_fp32(vmb_handle* h, const StepParams& sp, long long n_tiles_x, cudaStream_t st) {
+  const size_t smem = step_fp32_smem<H, TP>(h->L);
+  static bool attr_set = false;
+  if (!attr_set) {
+    CUDA_TRY(h, cudaFuncSetAttribute(k_step_fp32<H, TP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  dim3 grid((unsigned)n_tiles_x, (unsigned)sp.B);
+  k_step_fp32<H, TP><<<grid, 128, smem, st>>>(sp, h->L);
+  CUDA_TRY(h, cudaGetLastError());
+  return VMB_OK;
+}
+
+static int dispatch_fp32(vmb_handle* h, const StepParams& sp, cudaStream_t st) {
+  const int TP = (h->H == 32) ? 128 : (h->H == 256 ? 32 : 64);
+  if (sp.S > TP) return fail(h, VMB_E_UNSUPPORTED, "fp32 step kernel: n_samples exceeds the tile size for this hidden size");
+  const int nr = TP / sp.S;
+  const long long tiles = ((long long)sp.R + nr - 1) / nr;
+  if (tiles > 0x7fffffffLL || sp.B > 65535) return fail(h, VMB_E_ARG, "grid too large");
+  switch (h->H) {
+    case 32:  return launch_fp32<32, 128>(h, sp, tiles, st);
+    case 64:  return launch_fp32<64, 64>(h, sp, tiles, st);
+    case 128: return launch_fp32<128, 64>(h, sp, tiles, st);
+    case 256: return launch_fp32<256, 32>(h, sp, tiles, st);
+  }
+  return fail(h, VMB_E_UNSUPPORTED, "unsupported hidden size");
+}
+
+extern "C" {
+
+const char* vmb_version(void) { return "vmap_b200 0.1 (sm_100a)"; }
+
+int vmb_param_count(int hidden, int n_freq) {
+  if (hidden <= 0 || n_freq < 4 || n_freq > VMB_MAX_FREQ) return VMB_E_ARG;
+  return vmb_make_layout(hidden, n_freq).P;
+}
+int vmb_param_stride(int hidden, int n_freq) {
+  if (hidden <= 0 || n_freq < 4 || n_freq > VMB_MAX_FREQ) return VMB_E_ARG;
+  return vmb_make_layout(hidden, n_freq).stride;
+}
+int vmb_param_offsets(int hidden, int n_freq, int* offsets, int* sizes) {
+  if (hidden <= 0 || n_freq < 4 || n_freq > VMB_MAX_FREQ || !offsets || !sizes) return VMB_E_ARG;
+  const VmbLayout L = vmb_make_layout(hidden, n_freq);
+  const int H = hidden;
+  const int off[VMB_N_TENSORS] = {L.o_Win, L.o_bin, L.o_Wm1, L.o_bm1, L.o_Wcat, L.o_bcat, L.o_Wm2, L.o_bm2,
+                                  L.o_Wa, L.o_ba, L.o_Wcl, L.o_bcl, L.o_Woc, L.o_boc, L.o_B};
+  const int sz[VMB_N_TENSORS] = {H * VMB_E1, H, H * H, H, H * (H + VMB_E1), H, H * H, H,
+                                 H, 1, H * (H + L.e2), H, 3 * H, 3, VMB_NDIRS * 3};
+  for (int i = 0; i < VMB_N_TENSORS; ++i) { offsets[i] = off[i]; sizes[i] = sz[i]; }
+  return VMB_OK;
+}
+int vmb_image_bytes(int hidden, int n_freq) {
+  if (hidden == 32 && n_freq == 6) return umma_image_bytes();
+  return 0;
+}
+
+const char* vmb_last_error(const vmb_handle* h) { return h ? h->err.c_str() : g_err.c_str(); }
+
+int vmb_create(vmb_handle** out, int device, int max_obj, int hidden, int n_freq) {
+  if (!out || max_obj <= 0) return fail(nullptr, VMB_E_ARG, "vmb_create: bad arguments");
+  if (!(hidden == 32 || hidden == 64 || hidden == 128 || hidden == 256))
+    return fail(nullptr, VMB_E_UNSUPPORTED, "vmb_create: hidden must be 32, 64, 128 or 256");
+  if (n_freq < 4 || n_freq > VMB_MAX_FREQ) return fail(nullptr, VMB_E_ARG, "vmb_create: n_freq must be in [4,8]");
+  CUDA_TRY(nullptr, cudaSetDevice(device));
+  vmb_handle* h = new vmb_handle();
+  h->device = device; h->max_obj = max_obj; h->H = hidden; h->nfreq = n_freq;
+  h->L = vmb_make_layout(hidden, n_freq);
+  h->d_counts = nullptr; h->d_img_index = nullptr; h->img_halves = 0; h->umma_ok = false;
+  cudaError_t e = cudaMalloc(&h->d_counts, sizeof(int) * 4 * max_obj);
+  if (e != cudaSuccess) { delete h; return fail(nullptr, VMB_E_NOMEM, cudaGetErrorString(e)); }
+  if (hidden == 32 && n_freq == 6) {
+    std::vector<int> idx(h->L.P);
+    umma_fill_image_index(h->L, idx.data());
+    h->img_halves = umma_image_bytes() / 2;
+    e = cudaMalloc(&h->d_img_index, sizeof(int) * h->L.P);
+    if (e == cudaSuccess) e = cudaMemcpy(h->d_img_index, idx.data(), sizeof(int) * h->L.P, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { cudaFree(h->d_counts); delete h; return fail(nullptr, VMB_E_CUDA, cudaGetErrorString(e)); }
+    h->umma_ok = true;
+  }
+  *out = h;
+  return VMB_OK;
+}
+
+void vmb_destroy(vmb_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  if (h->d_counts) cudaFree(h->d_counts);
+  if (h->d_img_index) cudaFree(h->d_img_index);
+  delete h;
+}
+
+int vmb_mask_counts(vmb_handle* h, int n_obj, int n_rays, const unsigned char* sem, long long sem_stride,
+                    const unsigned char* mask_depth, long long mask_stride, int* out_counts, void* stream) {
+  if (!h || n_obj <= 0 || n_rays <= 0 || !sem || !mask_depth || !out_counts)
+    return fail(h, VMB_E_ARG, "vmb_mask_counts: bad arguments");
+  k_mask_counts<<<n_obj, 256, 0, (cudaStream_t)stream>>>(n_rays, sem, sem_stride, mask_depth, mask_stride,
+                                                         out_counts, nullptr);
+  CUDA_TRY(h, cudaGetLastError());
+  return VMB_OK;
+}
+
+int vmb_step(vmb_handle* h, const vmb_step_args* a, void* stream) {
+  if (!h || !a) return fail(h, VMB_E_ARG, "vmb_step: null argument");
+  if (a->n_obj <= 0 || a->n_obj > h->max_obj || a->n_rays <= 0 || a->n_samples <= 0 || a->n_samples > 32)
+    return fail(h, VMB_E_ARG, "vmb_step: bad n_obj / n_rays / n_samples (1 <= S <= 32)");
+  if (!a->pcs || !a->z_vals || !a->gt_depth || !a->gt_colour || !a->sem || !a->mask_depth || !a->params ||
+      !a->scale || !a->loss_terms || (a->backward && !a->grads))
+    return fail(h, VMB_E_ARG, "vmb_step: missing tensor pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int* counts = a->counts;
+  if (!counts) {
+    k_mask_counts<<<a->n_obj, 256, 0, st>>>(a->n_rays, a->sem, a->sem_stride, a->mask_depth, a->mask_stride,
+                                            h->d_counts, a->loss_terms);
+    CUDA_TRY(h, cudaGetLastError());
+    counts = h->d_counts;
+  } else {
+    CUDA_TRY(h, cudaMemsetAsync(a->loss_terms, 0, sizeof(float) * 4 * a->n_obj, st));
+  }
+  int impl = a->impl;
+  const bool umma_possible = h->umma_ok && a->image != nullptr && a->n_samples <= UMMA_MAX_S;
+  if (impl == VMB_IMPL_AUTO) impl = umma_possible ? VMB_IMPL_UMMA : VMB_IMPL_FP32;
+  StepParams sp;
+  memset(&sp, 0, sizeof(sp));
+  sp.B = a->n_obj; sp.R = a->n_rays; sp.S = a->n_samples;
+  sp.pcs = a->pcs; sp.pcs_stride = a->pcs_stride;
+  sp.z = a->z_vals; sp.z_stride = a->z_stride;
+  sp.gt_depth = a->gt_depth; sp.gt_depth_stride = a->gt_depth_stride;
+  sp.gt_colour = a->gt_colour; sp.gt_colour_stride = a->gt_colour_stride;
+  sp.sem = a->sem; sp.sem_stride = a->sem_stride;
+  sp.mask = a->mask_depth; sp.mask_stride = a->mask_stride;
+  sp.params = a->params; sp.scale = a->scale; sp.grads = a->grads; sp.loss_terms = a->loss_terms;
+  sp.r_depth = a->r_depth; sp.r_var = a->r_var; sp.r_colour = a->r_colour; sp.r_opacity = a->r_opacity;
+  sp.counts = counts; sp.cs = a->colour_scaling; sp.os = a->opacity_scaling; sp.backward = a->backward;
+  if (impl == VMB_IMPL_UMMA) {
+    if (!umma_possible) return fail(h, VMB_E_UNSUPPORTED, "vmb_step: UMMA path needs hidden=32, n_freq=6, an image and S<=16");
+    std::string err;
+    const int rc = umma_launch_step(h->L, sp, a->image, st, err);
+    if (rc != VMB_OK) return fail(h, rc, err);
+    return VMB_OK;
+  }
+  if (impl != VMB_IMPL_FP32) return fail(h, VMB_E_ARG, "vmb_step: unknown impl");
+  return dispatch_fp32(h, sp, st);
+}
+
+int vmb_forward(vmb_handle* h, const vmb_forward_args* a, void* stream) {
+  if (!h || !a || a->n_obj <= 0 || a->n_obj > h->max_obj || a->n_points <= 0 || !a->points || !a->params ||
+      !a->scale || !a->alpha || !a->colour)
+    return fail(h, VMB_E_ARG, "vmb_forward: bad arguments");
+  StepParams sp;
+  memset(&sp, 0, sizeof(sp));
+  if (a->n_points > 0x7fffffffLL) return fail(h, VMB_E_ARG, "vmb_forward: too many points per call");
+  sp.B = a->n_obj; sp.R = (int)a->n_points; sp.S = 1;
+  sp.pcs = a->points; sp.pcs_stride = a->points_stride;
+  sp.params = a->params; sp.scale = a->scale;
+  sp.fwd_only = 1;
+  sp.out_alpha = a->alpha; sp.alpha_stride = a->alpha_stride;
+  sp.out_colour = a->colour; sp.colour_stride = a->colour_stride;
+  return dispatch_fp32(h, sp, (cudaStream_t)stream);
+}
+
+int vmb_adam(vmb_handle* h, const vmb_adam_args* a, void* stream) {
+  if (!h || !a || a->n_obj <= 0 || a->n_obj > h->max_obj || a->step < 1 || !a->params || !a->grads ||
+      !a->exp_avg || !a->exp_avg_sq)
+    return fail(h, VMB_E_ARG, "vmb_adam: bad arguments");
+  if (a->image && !h->umma_ok) return fail(h, VMB_E_UNSUPPORTED, "vmb_adam: no fp16 image for this hidden size");
+  AdamParams p;
+  memset(&p, 0, sizeof(p));
+  p.n = (long long)a->n_obj * h->L.stride; p.stride = h->L.stride; p.P = h->L.P; p.B = a->n_obj;
+  p.p = a->params; p.g = a->grads; p.m = a->exp_avg; p.v = a->exp_avg_sq;
+  p.image = (__half*)a->image; p.img_index = h->d_img_index; p.img_halves = h->img_halves;
+  p.loss_terms = a->loss_terms; p.status = a->status;
+  // scalars exactly as torch.optim.adamw._single_tensor_adamw forms them (python doubles)
+  const double lr = a->lr, b1 = a->beta1, b2 = a->beta2;
+  p.lr_wd = (float)(1.0 - lr * (double)a->weight_decay);
+  p.one_m_b1 = (float)(1.0 - b1);
+  p.b2 = (float)b2;
+  p.one_m_b2 = (float)(1.0 - b2);
+  const double bc1 = 1.0 - std::pow(b1, (double)a->step);
+  const double bc2 = 1.0 - std::pow(b2, (double)a->step);
+  p.step_size = (float)(lr / bc1);
+  p.bc2_sqrt = (float)std::sqrt(bc2);
+  p.eps = a->eps;
+  p.zero_grads = a->zero_grads;
+  const long long n4 = p.n / 4;
+  const int blocks = (int)((n4 + 255) / 256);
+  k_adamw<<<blocks, 256, 0, (cudaStream_t)stream>>>(p);
+  CUDA_TRY(h, cudaGetLastError());
+  return VMB_OK;
+}
+
+int vmb_build_image(vmb_handle* h, int n_obj, const float* params, void* image, void* stream) {
+  if (!h || n_obj <= 0 || n_obj > h->max_obj || !params || !image) return fail(h, VMB_E_ARG, "vmb_build_image: bad arguments");
+  if (!h->umma_ok) return fail(h, VMB_E_UNSUPPORTED, "vmb_build_image: no fp16 image for this hidden size");
+  cudaStream_t st = (cudaStream_t)stream;
+  CUDA_TRY(h, cudaMemsetAsync(image, 0, (size_t)n_obj * h->img_halves * 2, st));
+  const long long n = (long long)n_obj * h->L.stride;
+  k_build_image<<<(int)((n + 255) / 256), 256, 0, st>>>(n_obj, h->L.stride, h->L.P, params, (__half*)image,
+                                                        h->d_img_index, h->img_halves);
+  CUDA_TRY(h, cudaGetLastError());
+  return VMB_OK;
+}
+
+int vmb_sample(vmb_handle* h, const vmb_sample_args* a, void* stream) {
+  if (!h || !a || a->n_obj <= 0 || a->n_frames <= 0 || a->n_pix <= 0)
+    return fail(h, VMB_E_ARG, "vmb_sample: bad arguments");
+  if (a->n_bins_cam2surface < 1 || a->n_bins < 1 || a->n_bins_cam2surface + a->n_bins > 32)
+    return fail(h, VMB_E_ARG, "vmb_sample: need 1 <= n1, n2 and n1+n2 <= 32");
+  if (!a->rgbs || !a->depths || !a->t_wc || !a->bbox || !a->n_keyframes || !a->latest_kf || !a->rays_dir ||
+      !a->bin_limits || !a->pcs || !a->z_vals || !a->gt_depth || !a->gt_colour || !a->sem || !a->mask_depth)
+    return fail(h, VMB_E_ARG, "vmb_sample: missing tensor pointer");
+  SampleParams p;
+  memset(&p, 0, sizeof(p));
+  p.B = a->n_obj; p.n_frames = a->n_frames; p.n_pix = a->n_pix; p.n1 = a->n_bins_cam2surface; p.n2 = a->n_bins;
+  p.W = a->width; p.Hh = a->height; p.min_bound = a->min_bound; p.eps = a->surface_eps; p.oeps = a->stop_eps;
+  p.rgbs = a->rgbs; p.depths = a->depths; p.t_wc = a->t_wc; p.bbox = a->bbox; p.n_kf = a->n_keyframes;
+  p.latest = a->latest_kf; p.rays_dir = a->rays_dir; p.lim = a->bin_limits; p.seed = a->seed; p.offset = a->offset;
+  p.inj_kf = a->inj_kf; p.inj_u_w = a->inj_u_w; p.inj_u_h = a->inj_u_h; p.inj_u_z = a->inj_u_z; p.inj_nrm = a->inj_nrm;
+  p.pcs = a->pcs; p.z = a->z_vals; p.gt_depth = a->gt_depth; p.gt_colour = a->gt_colour; p.rgb_u8 = a->gt_rgb_u8;
+  p.sem = a->sem; p.mask = a->mask_depth;
+  k_sample<<<a->n_obj, 512, 0, (cudaStream_t)stream>>>(p);
+  CUDA_TRY(h, cudaGetLastError());
+  return VMB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,207 @@
+"""Packed ensemble state + the fused training step (the package's public step API).
+
+One ``VmapEnsemble`` owns, for a stack of ``n_obj`` object MLPs on one GPU:
+``params | grads | exp_avg | exp_avg_sq`` as ``[n_obj, stride]`` fp32 blocks, the fp16
+tensor-core weight image, per-object scales, loss terms and the status word.  It replaces
+what ``utils.update_vmap`` + ``torch.optim.AdamW`` hold in the reference
+(utils.py:30-34, train.py:67) and runs train.py:293-326 as three kernel launches
+(mask counts, fused forward+loss+backward, fused AdamW).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional
+
+import torch
+
+from . import _lib
+from .layout import ALL_KEYS, host_offsets, tensor_shapes
+
+
+class LossExplode(RuntimeError):
+    """The reference prints 'loss explode' and exit(-1)s (render_rays.py:88-90);
+    here the update is skipped on the device and this is raised at the next check."""
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class VmapEnsemble:
+    def __init__(self, n_obj: int, hidden: int = 32, n_unidir_funcs: int = 5, scale=2.0,
+                 device="cuda:0", lr: float = 1e-3, weight_decay: float = 0.013,
+                 betas=(0.9, 0.999), eps: float = 1e-8, impl: str = "auto",
+                 colour_scaling: float = 5.0, opacity_scaling: float = 10.0):
+        self.lib = _lib.lib()
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise _lib.VmbError("VmapEnsemble needs a CUDA device: there is no CPU fallback")
+        self.n_obj, self.hidden, self.n_unidir_funcs = n_obj, hidden, n_unidir_funcs
+        self.n_freq = n_unidir_funcs + 1
+        self.lr, self.weight_decay, self.betas, self.eps = lr, weight_decay, betas, eps
+        self.impl = impl
+        self.colour_scaling, self.opacity_scaling = colour_scaling, opacity_scaling
+        self.count, self.stride, self.offsets, self.sizes = _lib.param_layout(hidden, self.n_freq)
+        assert (self.count, self.stride, self.offsets, self.sizes) == host_offsets(hidden, n_unidir_funcs)
+        self.shapes = tensor_shapes(hidden, n_unidir_funcs)
+        dev = self.device
+        with torch.cuda.device(dev):
+            self._handle = C.c_void_p()
+            _lib.check(None, self.lib.vmb_create(C.byref(self._handle), dev.index or 0, n_obj, hidden, self.n_freq),
+                       "vmb_create")
+        f32 = dict(dtype=torch.float32, device=dev)
+        self.params = torch.zeros(n_obj, self.stride, **f32)
+        self.grads = torch.zeros(n_obj, self.stride, **f32)
+        self.exp_avg = torch.zeros(n_obj, self.stride, **f32)
+        self.exp_avg_sq = torch.zeros(n_obj, self.stride, **f32)
+        self.image_bytes = self.lib.vmb_image_bytes(hidden, self.n_freq)
+        self.image = torch.zeros(n_obj, self.image_bytes, dtype=torch.uint8, device=dev) if self.image_bytes else None
+        sc = torch.as_tensor(scale, dtype=torch.float32)
+        self.scale = (sc.expand(n_obj) if sc.dim() == 0 else sc).to(dev).contiguous().clone()
+        self.loss_terms = torch.zeros(n_obj, 4, **f32)
+        self.status = torch.zeros(4, dtype=torch.int32, device=dev)
+        self.step_count = 0
+
+    def __del__(self):
+        try:
+            if getattr(self, "_handle", None):
+                self.lib.vmb_destroy(self._handle)
+                self._handle = None
+        except Exception:
+            pass
+
+    # ---- stacked views (what update_vmap returns as `params`, utils.py:31) ---------------
+    def view(self, key: str, block: Optional[torch.Tensor] = None) -> torch.Tensor:
+        i = ALL_KEYS.index(key)
+        blk = self.params if block is None else block
+        return blk[:, self.offsets[i]:self.offsets[i] + self.sizes[i]].view((self.n_obj,) + self.shapes[key])
+
+    def stacked(self, block: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
+        return {k: self.view(k, block) for k in ALL_KEYS}
+
+    def load_stacked(self, tensors: Dict[str, torch.Tensor], reset_optimizer: bool = True):
+        """Copy stacked [n_obj, *shape] tensors in.  ``reset_optimizer`` reproduces the
+        reference's behaviour of starting Adam from scratch whenever update_vmap
+        re-stacks."""
+        with torch.no_grad():
+            for k in ALL_KEYS:
+                self.view(k).copy_(tensors[k].to(self.device, torch.float32))
+        if reset_optimizer:
+            self.reset_optimizer()
+        self.refresh_image()
+
+    def reset_optimizer(self):
+        self.exp_avg.zero_(); self.exp_avg_sq.zero_(); self.grads.zero_()
+        self.step_count = 0
+
+    def refresh_image(self):
+        if self.image is not None:
+            with torch.cuda.device(self.device):
+                _lib.check(self._handle, self.lib.vmb_build_image(self._handle, self.n_obj, _ptr(self.params),
+                                                                  _ptr(self.image), _stream()), "vmb_build_image")
+
+    # ---- kernels ----------------------------------------------------------------------------
+    def _step_args(self, batch, backward: bool, outputs=None, impl: Optional[str] = None, counts=None):
+        pcs, z = batch["pcs"], batch["z"]
+        B, R, S = pcs.shape[0], pcs.shape[1], pcs.shape[2]
+        assert B == self.n_obj and pcs.shape[3] == 3 and tuple(z.shape) == (B, R, S)
+        gd, gc, sem, md = batch["gt_depth"], batch["gt_colour"], batch["sem"], batch["mask_depth"]
+        for t, dt in ((pcs, torch.float32), (z, torch.float32), (gd, torch.float32), (gc, torch.float32)):
+            assert t.dtype == dt and t.device == self.device
+        assert sem.dtype == torch.uint8 and md.dtype in (torch.bool, torch.uint8)
+        # per-object slices of a bigger tensor are fine as long as each object's block is dense
+        for t, inner in ((pcs, R * S * 3), (z, R * S), (gd, R), (gc, R * 3), (sem, R), (md, R)):
+            assert t[0].is_contiguous(), "per-object block must be contiguous"
+        a = _lib.StepArgs()
+        a.n_obj, a.n_rays, a.n_samples = B, R, S
+        a.impl = _lib.VMB_IMPL[impl or self.impl]
+        a.pcs, a.pcs_stride = _ptr(pcs), pcs.stride(0) if B > 1 else R * S * 3
+        a.z_vals, a.z_stride = _ptr(z), z.stride(0) if B > 1 else R * S
+        a.gt_depth, a.gt_depth_stride = _ptr(gd), gd.stride(0) if B > 1 else R
+        a.gt_colour, a.gt_colour_stride = _ptr(gc), gc.stride(0) if B > 1 else R * 3
+        a.sem, a.sem_stride = _ptr(sem), sem.stride(0) if B > 1 else R
+        a.mask_depth, a.mask_stride = _ptr(md), md.stride(0) if B > 1 else R
+        a.params, a.image, a.scale = _ptr(self.params), _ptr(self.image), _ptr(self.scale)
+        a.grads, a.loss_terms = _ptr(self.grads), _ptr(self.loss_terms)
+        if outputs is not None:
+            a.r_depth, a.r_var = _ptr(outputs["depth"]), _ptr(outputs["var"])
+            a.r_colour, a.r_opacity = _ptr(outputs["colour"]), _ptr(outputs["opacity"])
+        a.counts = _ptr(counts)
+        a.colour_scaling, a.opacity_scaling = self.colour_scaling, self.opacity_scaling
+        a.backward = 1 if backward else 0
+        return a
+
+    def forward_backward(self, batch, outputs=None, backward: bool = True, impl: Optional[str] = None,
+                         counts: Optional[torch.Tensor] = None):
+        """K0 + K1: accumulates into ``self.grads`` and overwrites ``self.loss_terms``."""
+        a = self._step_args(batch, backward, outputs, impl, counts)
+        with torch.cuda.device(self.device):
+            _lib.check(self._handle, self.lib.vmb_step(self._handle, C.byref(a), _stream()), "vmb_step")
+
+    def mask_counts(self, batch) -> torch.Tensor:
+        sem, md = batch["sem"], batch["mask_depth"]
+        B, R = sem.shape
+        out = torch.empty(B, 4, dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self._handle, self.lib.vmb_mask_counts(
+                self._handle, B, R, _ptr(sem), sem.stride(0) if B > 1 else R,
+                _ptr(md), md.stride(0) if B > 1 else R, _ptr(out), _stream()), "vmb_mask_counts")
+        return out
+
+    def adam_step(self, guard_loss: bool = True):
+        """K2: AdamW over the whole block + zero_grad (+ fp16 image refresh)."""
+        self.step_count += 1
+        a = _lib.AdamArgs()
+        a.n_obj, a.step = self.n_obj, self.step_count
+        a.params, a.grads = _ptr(self.params), _ptr(self.grads)
+        a.exp_avg, a.exp_avg_sq = _ptr(self.exp_avg), _ptr(self.exp_avg_sq)
+        a.image = _ptr(self.image)
+        a.loss_terms = _ptr(self.loss_terms) if guard_loss else None
+        a.status = _ptr(self.status)
+        a.lr, a.beta1, a.beta2, a.eps = self.lr, self.betas[0], self.betas[1], self.eps
+        a.weight_decay, a.zero_grads = self.weight_decay, 1
+        with torch.cuda.device(self.device):
+            _lib.check(self._handle, self.lib.vmb_adam(self._handle, C.byref(a), _stream()), "vmb_adam")
+
+    def step(self, batch, impl: Optional[str] = None) -> torch.Tensor:
+        """One optimisation step (train.py:293-326). Returns the summed loss (device scalar)."""
+        self.forward_backward(batch, impl=impl)
+        self.adam_step()
+        return self.loss_terms[:, 3].sum()
+
+    def render(self, batch, impl: Optional[str] = None):
+        """Forward + render only: (depth [B,R], var [B,R], colour [B,R,3], opacity [B,R])."""
+        B, R = batch["gt_depth"].shape
+        f32 = dict(dtype=torch.float32, device=self.device)
+        out = {"depth": torch.empty(B, R, **f32), "var": torch.empty(B, R, **f32),
+               "colour": torch.empty(B, R, 3, **f32), "opacity": torch.empty(B, R, **f32)}
+        self.forward_backward(batch, outputs=out, backward=False, impl=impl)
+        return out["depth"], out["var"], out["colour"], out["opacity"]
+
+    def eval_points(self, points: torch.Tensor):
+        """Forward only on raw points [B,N,3] -> alpha [B,N], colour [B,N,3] (trainer.py:77-90)."""
+        B, N, _ = points.shape
+        assert B == self.n_obj and points.is_contiguous() and points.dtype == torch.float32
+        alpha = torch.empty(B, N, dtype=torch.float32, device=self.device)
+        colour = torch.empty(B, N, 3, dtype=torch.float32, device=self.device)
+        a = _lib.ForwardArgs()
+        a.n_obj, a.n_points = B, N
+        a.points, a.points_stride = _ptr(points), N * 3
+        a.params, a.scale = _ptr(self.params), _ptr(self.scale)
+        a.alpha, a.alpha_stride = _ptr(alpha), N
+        a.colour, a.colour_stride = _ptr(colour), N * 3
+        with torch.cuda.device(self.device):
+            _lib.check(self._handle, self.lib.vmb_forward(self._handle, C.byref(a), _stream()), "vmb_forward")
+        return alpha, colour
+
+    def check_status(self):
+        """Host sync: raise if the device flagged a loss explosion / non-finite loss."""
+        st = int(self.status[0].item())
+        if st & _lib.VMB_ST_LOSS_EXPLODE:
+            raise LossExplode("loss explode (a per-object loss term exceeded 1e5); update skipped")
+        if st & _lib.VMB_ST_NONFINITE:
+            raise LossExplode("non-finite loss; update skipped")

@@ -1,0 +1,108 @@
+"""Batched depth-guided ray sampler (K3) -- host side.
+
+Replaces the per-object Python loop of train.py:208-218 over
+``sceneObject.get_training_samples`` (vmap.py:319-459) and the stack + /255 of
+train.py:255-260 with one kernel launch for all objects of the frame.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Sequence
+
+import torch
+
+from . import _lib
+
+
+@dataclass
+class KeyframeSet:
+    """The per-object buffers the sampler reads (sceneObject fields, vmap.py:137-176)."""
+    rgbs_batch: torch.Tensor      # [KF,W,H,4] u8 (rgb + state)
+    depth_batch: torch.Tensor     # [KF,W,H] f32
+    t_wc_batch: torch.Tensor      # [KF,4,4] f32
+    bbox: torch.Tensor            # [KF,4] f32
+    n_keyframes: int
+    latest_kf: Sequence[int]      # lastest_kf_queue[-2:]
+
+
+def _p(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+class BatchedSampler:
+    def __init__(self, device="cuda:0", n_bins_cam2surface=1, n_bins=9, surface_eps=0.1, stop_eps=0.05,
+                 min_bound=0.0, max_obj=1024):
+        self.lib = _lib.lib()
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise _lib.VmbError("BatchedSampler needs a CUDA device: there is no CPU fallback")
+        self.n1, self.n2 = n_bins_cam2surface, n_bins
+        self.eps, self.oeps, self.min_bound = surface_eps, stop_eps, min_bound
+        self._handle = C.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(None, self.lib.vmb_create(C.byref(self._handle), self.device.index or 0, max_obj, 32, 6),
+                       "vmb_create")
+        lim = torch.zeros(3, 33)
+        for row, n in enumerate((self.n1 + self.n2, self.n1, self.n2)):
+            lim[row, :n + 1] = torch.linspace(0, 1, n + 1, dtype=torch.float32)     # vmap.py:48
+        self.bin_limits = lim.to(self.device)
+        self._keep = None
+
+    def __del__(self):
+        try:
+            if getattr(self, "_handle", None):
+                self.lib.vmb_destroy(self._handle)
+                self._handle = None
+        except Exception:
+            pass
+
+    def sample(self, objects: List[KeyframeSet], n_frames: int, n_pix: int, rays_dir: torch.Tensor,
+               seed: int = 0, offset: int = 0, inject: Optional[Dict[str, torch.Tensor]] = None,
+               want_u8: bool = False) -> Dict[str, torch.Tensor]:
+        dev = self.device
+        B = len(objects)
+        N, S = n_frames * n_pix, self.n1 + self.n2
+        W, H = objects[0].rgbs_batch.shape[1], objects[0].rgbs_batch.shape[2]
+        for o in objects:
+            assert o.rgbs_batch.is_contiguous() and o.depth_batch.is_contiguous()
+            assert o.t_wc_batch.is_contiguous() and o.bbox.is_contiguous()
+            assert o.rgbs_batch.dtype == torch.uint8 and o.depth_batch.dtype == torch.float32
+            assert o.rgbs_batch.device == dev
+        ptrs = torch.tensor([[o.rgbs_batch.data_ptr(), o.depth_batch.data_ptr(), o.t_wc_batch.data_ptr(),
+                              o.bbox.data_ptr()] for o in objects], dtype=torch.int64).t().contiguous().to(dev)
+        nkf = torch.tensor([o.n_keyframes for o in objects], dtype=torch.int32, device=dev)
+        latest = torch.tensor([(list(o.latest_kf) + [0, 0])[:2] if len(o.latest_kf) >= 2
+                               else [o.latest_kf[0] if len(o.latest_kf) else 0] * 2 for o in objects],
+                              dtype=torch.int32, device=dev)
+        out = {
+            "pcs": torch.empty(B, N, S, 3, dtype=torch.float32, device=dev),
+            "z": torch.empty(B, N, S, dtype=torch.float32, device=dev),
+            "gt_depth": torch.empty(B, N, dtype=torch.float32, device=dev),
+            "gt_colour": torch.empty(B, N, 3, dtype=torch.float32, device=dev),
+            "sem": torch.empty(B, N, dtype=torch.uint8, device=dev),
+            "mask_depth": torch.empty(B, N, dtype=torch.bool, device=dev),
+        }
+        if want_u8:
+            out["gt_rgb_u8"] = torch.empty(B, N, 3, dtype=torch.uint8, device=dev)
+        a = _lib.SampleArgs()
+        a.n_obj, a.n_frames, a.n_pix = B, n_frames, n_pix
+        a.n_bins_cam2surface, a.n_bins, a.width, a.height = self.n1, self.n2, W, H
+        a.min_bound, a.surface_eps, a.stop_eps = self.min_bound, self.eps, self.oeps
+        a.rgbs, a.depths, a.t_wc, a.bbox = _p(ptrs[0]), _p(ptrs[1]), _p(ptrs[2]), _p(ptrs[3])
+        a.n_keyframes, a.latest_kf = _p(nkf), _p(latest)
+        a.rays_dir, a.bin_limits = _p(rays_dir), _p(self.bin_limits)
+        a.seed, a.offset = seed, offset
+        if inject is not None:
+            inj = {k: v.to(dev).contiguous() for k, v in inject.items()}
+            a.inj_kf, a.inj_u_w, a.inj_u_h = _p(inj["kf"]), _p(inj["u_w"]), _p(inj["u_h"])
+            a.inj_u_z, a.inj_nrm = _p(inj["u_z"]), _p(inj["nrm"])
+            self._keep = inj
+        a.pcs, a.z_vals, a.gt_depth, a.gt_colour = _p(out["pcs"]), _p(out["z"]), _p(out["gt_depth"]), _p(out["gt_colour"])
+        a.gt_rgb_u8 = _p(out.get("gt_rgb_u8"))
+        a.sem, a.mask_depth = _p(out["sem"]), _p(out["mask_depth"])
+        with torch.cuda.device(dev):
+            _lib.check(self._handle, self.lib.vmb_sample(
+                self._handle, C.byref(a), C.c_void_p(torch.cuda.current_stream().cuda_stream)), "vmb_sample")
+        self._keep = (self._keep, ptrs, nkf, latest)      # alive until the next call (async launch)
+        return out
