@@ -69,6 +69,7 @@ __global__ void __launch_bounds__(256) k_adamw(AdamParams a) {
       if (e + j < a.P) {
         const int t = a.img_index[e + j];
         if (t >= 0) img[t] = __float2half_rn(pp[j]);
+        else if (t <= -2) reinterpret_cast<float*>(img)[-(t + 2)] = pp[j];
       }
     }
   }
@@ -83,4 +84,5 @@ __global__ void __launch_bounds__(256) k_build_image(int B, int stride, int P, c
   if (e >= P) return;
   const int t = img_index[e];
   if (t >= 0) image[(size_t)b * img_halves + t] = __float2half_rn(p[i]);
+  else if (t <= -2) reinterpret_cast<float*>(image + (size_t)b * img_halves)[-(t + 2)] = p[i];
 }

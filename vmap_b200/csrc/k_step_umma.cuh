@@ -1,11 +1,682 @@
-// placeholder until the tcgen05 kernel lands
+// K1 (tensor-core flavour): fused PE -> MLP -> render -> loss -> backward for H = 32,
+// fp16 operands / fp32 accumulate on the 5th-gen tensor cores (tcgen05.mma, TMEM
+// accumulators), weights staged per object with one bulk async copy (TMA engine).
+//
+// CTA = 288 threads: two "point groups" of 128 threads (one thread = one sample point =
+// one TMEM lane) plus one MMA-issuer warp.  Each group walks its tile (up to 128 points =
+// whole rays) through 12 MMA stages in lock-step: threads write the next operand rows to
+// shared memory, arrive on the group's request mbarrier, the issuer thread issues the
+// stage's tcgen05.mma batch and commits to the group's done mbarrier, threads read the
+// accumulator back with tcgen05.ld.  The two groups run out of phase, so one group's
+// epilogue overlaps the other's MMAs.  Weight gradients accumulate in TMEM across all the
+// tiles a CTA owns for an object and are flushed once (fp32 atomics) per (CTA, object).
+//
+// Shared-memory operand layout: SWIZZLE_NONE 8x8 core matrices.  An activation block is
+// [feature-group (8 feats)][point][8 feats] halves, i.e. element (p, f) sits at
+// (f/8)*2048 + p*16 + (f%8)*2.  The same bytes serve as a K-major A operand (forward /
+// dgrad: M = points, K = features) and as an MN-major operand (wgrad: M or N = features,
+// K = points) -- only the descriptor's LBO/SBO swap roles.  Weight matrices W[o][k] are
+// stored the same way, (k/8)*512 + o*16 + (k%8)*2, and serve as K-major B (forward) and
+// MN-major B (dgrad: N = k, K = o).
+//
+// Feature order inside the embedding blocks is chosen for the PE recurrence (one sincos
+// per direction, then angle doubling), and each block carries a constant-1 column so the
+// bias gradients fall out of the wgrad MMAs; the weight image (written by the fused Adam
+// kernel) is permuted to match.  dY operands carry a static loss scale of 2^8.
+//
+// Reference arithmetic: embedding.py:82-91, model.py:54-85, render_rays.py:4-96,
+// loss.py:5-62 and their autograd backward (train.py:293-324).
 #pragma once
+#include <string>
 #include "common.cuh"
 #include "k_step_fp32.cuh"
-#include <string>
+#include "umma_ptx.cuh"
+
 #define UMMA_MAX_S 16
-static int umma_image_bytes() { return 32768; }
-static void umma_fill_image_index(const VmbLayout& L, int* idx) { for (int i = 0; i < L.P; ++i) idx[i] = -1; }
-static int umma_launch_step(const VmbLayout&, const StepParams&, const void*, cudaStream_t, std::string& err) {
-  err = "UMMA step kernel not built"; return -4;
+
+namespace um {
+
+constexpr int NT = 288;
+constexpr int FGB = 2048;                 // bytes of one 8-feature group for 128 points
+// feature-group index of each block inside a group's activation region
+constexpr int FG_HC = 0, FG_DH = 4, FG_FC1 = 6, FG_FC2 = 10, FG_E1 = 14, FG_FC3 = 26, FG_FC4 = 30, FG_E2 = 34;
+constexpr int FG_TOTAL = 40;
+constexpr int ACT_BYTES = FG_TOTAL * FGB;                 // 81920 per group
+// weight image (bytes)
+constexpr int IMG_WIN = 0, IMG_WM1 = 6144, IMG_WCAT = 8192, IMG_WM2 = 16384, IMG_WCL = 18432;
+constexpr int IMG_WA16 = 23552, IMG_WOC16 = 24576, IMG_F32 = 25600;
+// fp32 section (float index relative to IMG_F32)
+constexpr int F_BIN = 0, F_BM1 = 32, F_BCAT = 64, F_BM2 = 96, F_BCL = 128, F_BA = 160, F_BOC = 161, F_DIRS = 168;
+constexpr int IMG_BYTES = 26624;
+// shared memory map
+constexpr int SM_ACT0 = 0, SM_ACT1 = ACT_BYTES, SM_W = 2 * ACT_BYTES, SM_SC = SM_W + IMG_BYTES;
+constexpr int SC_BYTES = 5 * 128 * 4;                     // alpha, c0, c1, c2, z per point
+constexpr int SM_MISC = SM_SC + 2 * SC_BYTES;
+constexpr int SMEM_BYTES = SM_MISC + 256;
+// TMEM columns
+constexpr int WG_IN = 0, WG_M1 = 32, WG_CAT = 64, WG_M2 = 96, WG_CL = 128, WG_A = 160, WG_OC = 176;
+constexpr int ACC0 = 192, ACC_STRIDE = 160;               // per group: A[0,32) B[32,64) E[64,160)
+constexpr float LS = 256.0f, INV_LS = 1.0f / 256.0f, HMAX = 60000.0f;
+
+// ---- column maps ------------------------------------------------------------------------
+// emb1 block (96 cols): 0 = const 1, 1..3 = xyz/scale, 4..7 = dir 20 (k=0..3),
+// 8i+e (i=1..10) = dir 2(i-1)+e/4, k=e%4; 88..95 = 0.
+__host__ __device__ inline int emb1_col_to_j(int c) {     // -> reference emb index, -2 ones, -1 pad
+  if (c == 0) return -2;
+  if (c < 4) return c - 1;
+  if (c < 8) return 3 + (c - 4) * VMB_NDIRS + 20;
+  if (c >= 88) return -1;
+  const int i = c >> 3, e = c & 7;
+  return 3 + (e & 3) * VMB_NDIRS + 2 * (i - 1) + (e >> 2);
+}
+__host__ __device__ inline int j_to_emb1_col(int j) {
+  if (j < 3) return 1 + j;
+  const int k = (j - 3) / VMB_NDIRS, d = (j - 3) % VMB_NDIRS;
+  if (d == 20) return 4 + k;
+  return 8 * (d / 2 + 1) + (d & 1) * 4 + k;
+}
+// emb2 block (48 cols): 8i+e (i=0..4) = dir 4i+e/2, k=4+e%2; 40,41 = dir 20 (k=4,5); 42 = const 1.
+__host__ __device__ inline int emb2_col_to_j2(int c) {    // -> index into the reference's emb[87:], -2 ones, -1 pad
+  if (c == 42) return -2;
+  if (c > 42) return -1;
+  int d, k;
+  if (c >= 40) { d = 20; k = 4 + (c - 40); } else { d = 4 * (c >> 3) + ((c & 7) >> 1); k = 4 + (c & 1); }
+  return 3 + k * VMB_NDIRS + d - VMB_E1;
+}
+__host__ __device__ inline int j2_to_emb2_col(int j2) {
+  const int j = j2 + VMB_E1;
+  const int k = (j - 3) / VMB_NDIRS, d = (j - 3) % VMB_NDIRS;
+  if (d == 20) return 40 + (k - 4);
+  return 8 * (d / 4) + (d & 3) * 2 + (k - 4);
+}
+// half index of W[o][c] in a 32-row matrix / of W[j][o] in a 16-row (heads) matrix
+__host__ __device__ inline int widx32(int base_bytes, int o, int c) { return (base_bytes + (c >> 3) * 512 + o * 16 + (c & 7) * 2) >> 1; }
+__host__ __device__ inline int widx16(int base_bytes, int j, int o) { return (base_bytes + (o >> 3) * 256 + j * 16 + (o & 7) * 2) >> 1; }
+
+// wgrad accumulator (block, lane, out col) -> param index (or -1)
+__device__ __forceinline__ int wg_target(const VmbLayout& L, int blk, int lane, int o) {
+  switch (blk) {
+    case 0: {   // in_layer: lanes = emb1 cols
+      if (lane >= 96) return -1;
+      const int j = emb1_col_to_j(lane);
+      return j == -2 ? L.o_bin + o : (j < 0 ? -1 : L.o_Win + o * VMB_E1 + j);
+    }
+    case 1:     // mid1: lanes = fc1 | fc2 | emb1[0..64)
+      return lane < 32 ? L.o_Wm1 + o * 32 + lane : (lane == 64 ? L.o_bm1 + o : -1);
+    case 2: {   // cat_layer: lanes = fc2 | emb1
+      if (lane < 32) return L.o_Wcat + o * (32 + VMB_E1) + lane;
+      const int j = emb1_col_to_j(lane - 32);
+      return j == -2 ? L.o_bcat + o : (j < 0 ? -1 : L.o_Wcat + o * (32 + VMB_E1) + 32 + j);
+    }
+    case 3:     // mid2: lanes = fc3 | fc4 | emb2
+      return lane < 32 ? L.o_Wm2 + o * 32 + lane : (lane == 64 + 42 ? L.o_bm2 + o : -1);
+    case 4: {   // color_linear: lanes = fc4 | emb2
+      if (lane < 32) return L.o_Wcl + o * (32 + L.e2) + lane;
+      if (lane >= 80) return -1;
+      const int j2 = emb2_col_to_j2(lane - 32);
+      return j2 == -2 ? L.o_bcl + o : (j2 < 0 ? -1 : L.o_Wcl + o * (32 + L.e2) + 32 + j2);
+    }
+    default: {  // heads: cols 0..15 = WG_A (A = fc4 | emb2), cols 16..31 = WG_OC (A = hc | dh | fc1 | fc2 | emb1[0..16))
+      if (o < 16) {
+        if (o != 0) return -1;
+        return lane < 32 ? L.o_Wa + lane : (lane == 32 + 42 ? L.o_ba : -1);
+      }
+      const int c = o - 16;
+      if (c < 1 || c > 3) return -1;
+      return lane < 32 ? L.o_Woc + (c - 1) * 32 + lane : (lane == 112 ? L.o_boc + c - 1 : -1);
+    }
+  }
+}
+
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+  __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ float clamp_h(float x) { return fminf(fmaxf(x, -HMAX), HMAX); }
+
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(ptx::smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+// Bring-up safety net: a protocol bug traps (CUDA error) instead of hanging the GPU.
+#ifndef VMB_SPIN_LIMIT
+#define VMB_SPIN_LIMIT 50000000u
+#endif
+__device__ __forceinline__ void mbar_wait_or_trap(uint64_t* bar, uint32_t parity) {
+  for (uint32_t i = 0; i < VMB_SPIN_LIMIT; ++i)
+    if (ptx::mbar_try_wait(bar, parity)) return;
+  __trap();
+}
+__device__ __forceinline__ void group_bar(int g) { asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory"); }
+
+struct Misc {
+  uint64_t req[2], done[2], wbar;
+  uint32_t tmem_base;
+  int on[3];
+  int abort_flag;
+};
+
+// ---- the MMA issuer: one thread issues every tcgen05.mma of the CTA ---------------------
+struct Issuer {
+  uint32_t act[2], W, tm;
+  uint32_t wg_started;      // bit per wgrad accumulator: 0 -> first MMA overwrites
+
+  // descriptors
+  __device__ __forceinline__ uint64_t a_k(int g, int fg, int ks) const { return ptx::smem_desc(act[g] + fg * FGB + ks * 4096, 2048, 128); }
+  __device__ __forceinline__ uint64_t x_mn(int g, int fg, int ks) const { return ptx::smem_desc(act[g] + fg * FGB + ks * 256, 128, 2048); }
+  __device__ __forceinline__ uint64_t w_k(int off, int ks) const { return ptx::smem_desc(W + off + ks * 1024, 512, 128); }
+  __device__ __forceinline__ uint64_t w16_k(int off, int ks) const { return ptx::smem_desc(W + off + ks * 512, 256, 128); }
+  __device__ __forceinline__ uint64_t w_mn(int off, int ks) const { return ptx::smem_desc(W + off + ks * 256, 128, 512); }
+  __device__ __forceinline__ uint64_t w16_mn(int off) const { return ptx::smem_desc(W + off, 128, 256); }
+
+  __device__ __forceinline__ void wgrad(int g, int col, int bit, int fgA, int fgB, uint32_t idesc) {
+    uint32_t acc = (wg_started >> bit) & 1u;
+#pragma unroll
+    for (int ks = 0; ks < 8; ++ks) { ptx::umma_f16(tm + col, x_mn(g, fgA, ks), x_mn(g, fgB, ks), idesc, acc); acc = 1u; }
+    wg_started |= 1u << bit;
+  }
+
+  __device__ __forceinline__ void stage(int g, int st) {
+    constexpr uint32_t KK32 = ptx::idesc_f16(128, 32, 0, 0), KK16 = ptx::idesc_f16(128, 16, 0, 0);
+    constexpr uint32_t KM32 = ptx::idesc_f16(128, 32, 0, 1), KM48 = ptx::idesc_f16(128, 48, 0, 1), KM96 = ptx::idesc_f16(128, 96, 0, 1);
+    constexpr uint32_t MM32 = ptx::idesc_f16(128, 32, 1, 1), MM16 = ptx::idesc_f16(128, 16, 1, 1);
+    const uint32_t A = tm + ACC0 + g * ACC_STRIDE, B = A + 32, E = A + 64;
+    switch (st) {
+      case 0:   // in_layer: emb1 (K=96) -> A
+#pragma unroll
+        for (int ks = 0; ks < 6; ++ks) ptx::umma_f16(A, a_k(g, FG_E1, ks), w_k(IMG_WIN, ks), KK32, ks > 0);
+        break;
+      case 1:   // mid1: fc1 -> B
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) ptx::umma_f16(B, a_k(g, FG_FC1, ks), w_k(IMG_WM1, ks), KK32, ks > 0);
+        break;
+      case 2:   // cat_layer: [fc2 | emb1] (K=128) -> A
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) ptx::umma_f16(A, a_k(g, FG_FC2, ks), w_k(IMG_WCAT, ks), KK32, ks > 0);
+        break;
+      case 3:   // mid2: fc3 -> B
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) ptx::umma_f16(B, a_k(g, FG_FC3, ks), w_k(IMG_WM2, ks), KK32, ks > 0);
+        break;
+      case 4:   // color_linear: [fc4 | emb2] (K=80) -> A ; out_alpha: fc4 -> B[0..16) col 0
+#pragma unroll
+        for (int ks = 0; ks < 5; ++ks) ptx::umma_f16(A, a_k(g, FG_FC4, ks), w_k(IMG_WCL, ks), KK32, ks > 0);
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) ptx::umma_f16(B, a_k(g, FG_FC4, ks), w16_k(IMG_WA16, ks), KK16, ks > 0);
+        break;
+      case 5:   // out_color: hc -> B[0..16) cols 1..3 (accumulate onto alpha's tile)
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) ptx::umma_f16(B, a_k(g, FG_HC, ks), w16_k(IMG_WOC16, ks), KK16, 1u);
+        break;
+      case 6:   // d_hc = dhead @ W_oc -> A ; wgrad out_color, out_alpha
+        ptx::umma_f16(A, a_k(g, FG_DH, 0), w16_mn(IMG_WOC16), KM32, 0u);
+        wgrad(g, WG_OC, 6, FG_HC, FG_DH, MM16);
+        wgrad(g, WG_A, 5, FG_FC4, FG_DH, MM16);
+        break;
+      case 7:   // d_fc4 = dYc @ W_cl[:, :32] + dhead @ W_a -> B ; d_emb2 = dYc @ W_cl[:, 32:] -> E[0..48) ; wgrad color_linear
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) ptx::umma_f16(B, a_k(g, FG_HC, ks), w_mn(IMG_WCL, ks), KM32, ks > 0);
+        ptx::umma_f16(B, a_k(g, FG_DH, 0), w16_mn(IMG_WA16), KM32, 1u);
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) ptx::umma_f16(E, a_k(g, FG_HC, ks), w_mn(IMG_WCL + 4 * 512, ks), KM48, ks > 0);
+        wgrad(g, WG_CL, 4, FG_FC4, FG_HC, MM32);
+        break;
+      case 8:   // d_fc3 = dY4 @ W_m2 -> A ; wgrad mid2
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) ptx::umma_f16(A, a_k(g, FG_FC4, ks), w_mn(IMG_WM2, ks), KM32, ks > 0);
+        wgrad(g, WG_M2, 3, FG_FC3, FG_FC4, MM32);
+        break;
+      case 9:   // d_fc2 = dY3 @ W_cat[:, :32] -> B ; d_emb1 = dY3 @ W_cat[:, 32:] -> E ; wgrad cat_layer
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) ptx::umma_f16(B, a_k(g, FG_FC3, ks), w_mn(IMG_WCAT, ks), KM32, ks > 0);
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) ptx::umma_f16(E, a_k(g, FG_FC3, ks), w_mn(IMG_WCAT + 4 * 512, ks), KM96, ks > 0);
+        wgrad(g, WG_CAT, 2, FG_FC2, FG_FC3, MM32);
+        break;
+      case 10:  // d_fc1 = dY2 @ W_m1 -> A ; wgrad mid1
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) ptx::umma_f16(A, a_k(g, FG_FC2, ks), w_mn(IMG_WM1, ks), KM32, ks > 0);
+        wgrad(g, WG_M1, 1, FG_FC1, FG_FC2, MM32);
+        break;
+      default:  // 11: d_emb1 += dY1 @ W_in -> E ; wgrad in_layer
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) ptx::umma_f16(E, a_k(g, FG_FC1, ks), w_mn(IMG_WIN, ks), KM96, 1u);
+        wgrad(g, WG_IN, 0, FG_E1, FG_FC1, MM32);
+        break;
+    }
+  }
+};
+
+// per-direction sin/cos ladder: s[k] = sin(pi 2^k proj), c[k] = cos(...), k = 0..5
+__device__ __forceinline__ void sincos_ladder(float proj, float (&s)[6], float (&c)[6]) {
+  const float r = proj - 2.0f * rintf(0.5f * proj);          // exact: sin(pi x) has period 2
+  s[0] = __sinf(VMB_PI_F * r);
+  c[0] = __cosf(VMB_PI_F * r);
+#pragma unroll
+  for (int k = 1; k < 6; ++k) {
+    s[k] = 2.0f * s[k - 1] * c[k - 1];
+    c[k] = fmaf(-2.0f * s[k - 1], s[k - 1], 1.0f);
+  }
+}
+
+}  // namespace um
+
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(um::NT, 1)
+k_step_umma(StepParams a, VmbLayout L, const unsigned char* __restrict__ image, int tpo, int nr, long long T) {
+  using namespace um;
+  extern __shared__ __align__(1024) unsigned char smem[];
+  Misc* misc = reinterpret_cast<Misc*>(smem + SM_MISC);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int S = a.S, R = a.R;
+
+  if (tid == 0) {
+    ptx::mbar_init(&misc->req[0], 128); ptx::mbar_init(&misc->req[1], 128);
+    ptx::mbar_init(&misc->done[0], 1);  ptx::mbar_init(&misc->done[1], 1);
+    ptx::mbar_init(&misc->wbar, 1);
+    misc->abort_flag = 0;
+    ptx::mbar_init_fence();
+  }
+  if (warp == 8) { ptx::tmem_alloc(&misc->tmem_base, 512); ptx::tmem_relinquish(); }
+  if (tid < 3) {                      // render_rays.py:68-73: one empty mask anywhere zeroes the term for all
+    int on = 1;
+    for (int i = 0; i < a.B; ++i) on &= (a.counts[i * 4 + tid] != 0);
+    misc->on[tid] = on;
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tm = misc->tmem_base;
+
+  // this CTA's range of global tiles (tile = nr whole rays of one object)
+  const long long gt_begin = (T * blockIdx.x) / gridDim.x, gt_end = (T * (blockIdx.x + 1)) / gridDim.x;
+  const int n_stage = a.backward ? 12 : 6;
+  uint32_t wpar = 0;                  // weight-barrier parity (one completion per segment)
+  uint32_t ph = 0;                    // req/done parity of this thread's group
+  uint32_t iph[2] = {0u, 0u};         // issuer's view of the two groups' parities
+
+  for (long long gt = gt_begin; gt < gt_end;) {
+    const int b = (int)(gt / tpo);
+    const int t0 = (int)(gt - (long long)b * tpo);
+    const int t1 = (int)min((long long)tpo, (long long)t0 + (gt_end - gt));
+    gt += t1 - t0;
+
+    // ---- stage this object's weight image: one bulk copy global -> shared --------------
+    if (tid == 0) {
+      ptx::mbar_arrive_expect_tx(&misc->wbar, IMG_BYTES);
+      ptx::bulk_g2s(smem + SM_W, image + (size_t)b * IMG_BYTES, IMG_BYTES, &misc->wbar);
+    }
+    mbar_wait_or_trap(&misc->wbar, wpar);
+    wpar ^= 1;
+
+    if (warp == 8) {
+      // =========================== MMA issuer ===========================================
+      if (tid == 256) {
+        Issuer is;
+        is.act[0] = ptx::smem_u32(smem + SM_ACT0); is.act[1] = ptx::smem_u32(smem + SM_ACT1);
+        is.W = ptx::smem_u32(smem + SM_W); is.tm = tm; is.wg_started = 0;
+        int left[2], st[2] = {0, 0};
+        left[0] = (t1 - t0 + 1) / 2; left[1] = (t1 - t0) / 2;
+        uint32_t spins = 0;
+        while (left[0] > 0 || left[1] > 0) {
+          if (++spins > 4000000000u) __trap();
+#pragma unroll
+          for (int g = 0; g < 2; ++g) {
+            if (left[g] > 0 && mbar_test(&misc->req[g], iph[g])) {
+              ptx::tc_fence_after();
+              is.stage(g, st[g]);
+              ptx::umma_commit(&misc->done[g]);
+              iph[g] ^= 1;
+              if (++st[g] == n_stage) { st[g] = 0; --left[g]; }
+              spins = 0;
+            }
+          }
+        }
+      }
+    } else {
+      // =========================== point groups ==========================================
+      const int g = warp >> 2, tg = tid & 127;
+      unsigned char* act = smem + (g ? SM_ACT1 : SM_ACT0);
+      float* sc = reinterpret_cast<float*>(smem + SM_SC + g * SC_BYTES);      // [5][128]
+      const float* wf = reinterpret_cast<const float*>(smem + SM_W + IMG_F32);
+      const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+      const uint32_t tA = tm + ACC0 + g * ACC_STRIDE + lane_base, tB = tA + 32, tE = tA + 64;
+      const float scale_b = a.scale[b];
+      const float inv_nd = 1.f / ((float)a.counts[b * 4 + 0] + 1e-10f);
+      const float inv_no = 1.f / ((float)a.counts[b * 4 + 1] + 1e-10f);
+      const float inv_ns = 1.f / ((float)a.counts[b * 4 + 2] + 1e-10f);
+      const float on_d = misc->on[0] ? 1.f : 0.f, on_c = misc->on[1] ? 1.f : 0.f, on_o = misc->on[2] ? 1.f : 0.f;
+      float dBacc[63];
+#pragma unroll
+      for (int i = 0; i < 63; ++i) dBacc[i] = 0.f;
+      float ls_d = 0.f, ls_c = 0.f, ls_o = 0.f;
+
+#define STAGE_SYNC()                                   \
+  do {                                                 \
+    ptx::fence_async_smem();                           \
+    ptx::tc_fence_before();                            \
+    ptx::mbar_arrive(&misc->req[g]);                   \
+    mbar_wait_or_trap(&misc->done[g], ph);             \
+    ph ^= 1;                                           \
+    ptx::tc_fence_after();                             \
+  } while (0)
+
+      for (int t = t0 + g; t < t1; t += 2) {
+        const int r0 = t * nr;
+        const int rl = tg / S, sidx = tg - rl * S;
+        const bool pvalid = (tg < nr * S) && (r0 + rl < R);
+        // ---- E0: load point + positional embedding ------------------------------------
+        float t0x = 0.f, t1x = 0.f, t2x = 0.f, zz = 0.f;
+        if (pvalid) {
+          const size_t pi = (size_t)(r0 + rl) * S + sidx;
+          const float* pp = a.pcs + (size_t)b * a.pcs_stride + pi * 3;
+          const float isc = 1.0f / scale_b;
+          t0x = pp[0] * isc; t1x = pp[1] * isc; t2x = pp[2] * isc;
+          zz = a.z[(size_t)b * a.z_stride + pi];
+        }
+        sc[4 * 128 + tg] = zz;
+        // ray-thread inputs, fetched early (consumed at the render stage)
+        const bool is_ray = (tg < nr) && (r0 + tg < R);
+        float gd = 0.f, gc0 = 0.f, gc1 = 0.f, gc2 = 0.f; int sv = 0, mv = 0;
+        if (is_ray) {
+          const int ray = r0 + tg;
+          gd = a.gt_depth[(size_t)b * a.gt_depth_stride + ray];
+          const float* gcp = a.gt_colour + (size_t)b * a.gt_colour_stride + (size_t)ray * 3;
+          gc0 = gcp[0]; gc1 = gcp[1]; gc2 = gcp[2];
+          sv = a.sem[(size_t)b * a.sem_stride + ray];
+          mv = a.mask[(size_t)b * a.mask_stride + ray];
+        }
+        {
+          const float* Bd = wf + F_DIRS;
+          uint4* e1 = reinterpret_cast<uint4*>(act + FG_E1 * FGB + tg * 16);
+          uint4* e2 = reinterpret_cast<uint4*>(act + FG_E2 * FGB + tg * 16);
+          float s[6], c[6];
+          // direction 20 shares chunk 0 of emb1 with [1, x, y, z] and chunk 5 of emb2 with the const-1 column
+          sincos_ladder(fmaf(Bd[62], t2x, fmaf(Bd[61], t1x, Bd[60] * t0x)), s, c);
+          e1[0] = make_uint4(pack_h2(1.0f, t0x), pack_h2(t1x, t2x), pack_h2(s[0], s[1]), pack_h2(s[2], s[3]));
+          e2[5 * 128] = make_uint4(pack_h2(s[4], s[5]), pack_h2(1.0f, 0.f), 0u, 0u);
+          e1[11 * 128] = make_uint4(0u, 0u, 0u, 0u);
+          uint32_t hold[4];
+#pragma unroll
+          for (int i = 0; i < 10; ++i) {
+            float sa[6], ca[6], sb[6], cb[6];
+            const int d0 = 2 * i, d1 = 2 * i + 1;
+            sincos_ladder(fmaf(Bd[d0 * 3 + 2], t2x, fmaf(Bd[d0 * 3 + 1], t1x, Bd[d0 * 3] * t0x)), sa, ca);
+            sincos_ladder(fmaf(Bd[d1 * 3 + 2], t2x, fmaf(Bd[d1 * 3 + 1], t1x, Bd[d1 * 3] * t0x)), sb, cb);
+            e1[(i + 1) * 128] = make_uint4(pack_h2(sa[0], sa[1]), pack_h2(sa[2], sa[3]), pack_h2(sb[0], sb[1]), pack_h2(sb[2], sb[3]));
+            if ((i & 1) == 0) { hold[0] = pack_h2(sa[4], sa[5]); hold[1] = pack_h2(sb[4], sb[5]); }
+            else { e2[(i >> 1) * 128] = make_uint4(hold[0], hold[1], pack_h2(sa[4], sa[5]), pack_h2(sb[4], sb[5])); }
+          }
+          // zero this point's dhead row (cols 4..15 stay zero; 0..3 are written by the ray thread)
+          uint4* dh = reinterpret_cast<uint4*>(act + FG_DH * FGB + tg * 16);
+          dh[0] = make_uint4(0u, 0u, 0u, 0u); dh[128] = make_uint4(0u, 0u, 0u, 0u);
+        }
+        uint32_t m1, m2, m3, m4, mc;
+
+        // hidden-layer epilogue: acc + bias -> ReLU -> fp16 row (4 x 16 B), returns the sign mask
+#define EPI_RELU(TADDR, BIAS_OFF, FG, MASK)                                                    \
+  do {                                                                                         \
+    float v[32];                                                                               \
+    ptx::tmem_ld32(TADDR, v);                                                                  \
+    ptx::tmem_ld_wait();                                                                       \
+    uint32_t mk = 0;                                                                           \
+    _Pragma("unroll") for (int j = 0; j < 32; ++j) {                                           \
+      const float x = v[j] + wf[(BIAS_OFF) + j];                                               \
+      if (x > 0.f) { mk |= 1u << j; v[j] = x; } else v[j] = 0.f;                               \
+    }                                                                                          \
+    MASK = mk;                                                                                 \
+    uint4* dst = reinterpret_cast<uint4*>(act + (FG) * FGB + tg * 16);                         \
+    _Pragma("unroll") for (int q = 0; q < 4; ++q)                                              \
+      dst[q * 128] = make_uint4(pack_h2(v[8 * q], v[8 * q + 1]), pack_h2(v[8 * q + 2], v[8 * q + 3]), \
+                                pack_h2(v[8 * q + 4], v[8 * q + 5]), pack_h2(v[8 * q + 6], v[8 * q + 7])); \
+  } while (0)
+        // dgrad epilogue: dY = relu'(h) * acc -> fp16 row written over h
+#define EPI_DGRAD(TADDR, FG, MASK)                                                             \
+  do {                                                                                         \
+    float v[32];                                                                               \
+    ptx::tmem_ld32(TADDR, v);                                                                  \
+    ptx::tmem_ld_wait();                                                                       \
+    _Pragma("unroll") for (int j = 0; j < 32; ++j) v[j] = ((MASK >> j) & 1u) ? clamp_h(v[j]) : 0.f; \
+    uint4* dst = reinterpret_cast<uint4*>(act + (FG) * FGB + tg * 16);                         \
+    _Pragma("unroll") for (int q = 0; q < 4; ++q)                                              \
+      dst[q * 128] = make_uint4(pack_h2(v[8 * q], v[8 * q + 1]), pack_h2(v[8 * q + 2], v[8 * q + 3]), \
+                                pack_h2(v[8 * q + 4], v[8 * q + 5]), pack_h2(v[8 * q + 6], v[8 * q + 7])); \
+  } while (0)
+
+        STAGE_SYNC();                               // st0: in_layer
+        EPI_RELU(tA, F_BIN, FG_FC1, m1);
+        STAGE_SYNC();                               // st1: mid1
+        EPI_RELU(tB, F_BM1, FG_FC2, m2);
+        STAGE_SYNC();                               // st2: cat_layer
+        EPI_RELU(tA, F_BCAT, FG_FC3, m3);
+        STAGE_SYNC();                               // st3: mid2
+        EPI_RELU(tB, F_BM2, FG_FC4, m4);
+        STAGE_SYNC();                               // st4: color_linear + out_alpha
+        EPI_RELU(tA, F_BCL, FG_HC, mc);
+        STAGE_SYNC();                               // st5: out_color
+        {
+          float v[16];
+          ptx::tmem_ld16(tB, v);
+          ptx::tmem_ld_wait();
+          sc[0 * 128 + tg] = (v[0] + wf[F_BA]) * 10.0f;                      // model.py:77
+          sc[1 * 128 + tg] = vmb_sigmoid(v[1] + wf[F_BOC + 0]);              // model.py:83
+          sc[2 * 128 + tg] = vmb_sigmoid(v[2] + wf[F_BOC + 1]);
+          sc[3 * 128 + tg] = vmb_sigmoid(v[3] + wf[F_BOC + 2]);
+        }
+        group_bar(g);
+        // ---- volume render + loss + d(loss)/d(raw alpha, raw colour) on the ray threads --
+        if (is_ray) {
+          const int ray = r0 + tg, pb = tg * S;
+          float occ_[UMMA_MAX_S], T_[UMMA_MAX_S];
+          float Tr = 1.f, D = 0.f, O = 0.f, C0 = 0.f, C1 = 0.f, C2 = 0.f;
+          for (int s = 0; s < S; ++s) {
+            const int q = pb + s;
+            const float occ = vmb_sigmoid(sc[q]);
+            const float w = occ * Tr;
+            occ_[s] = occ; T_[s] = Tr;
+            D = fmaf(w, sc[4 * 128 + q], D); O += w;
+            C0 = fmaf(w, sc[1 * 128 + q], C0); C1 = fmaf(w, sc[2 * 128 + q], C1); C2 = fmaf(w, sc[3 * 128 + q], C2);
+            Tr *= (1.f - occ + 1e-10f);
+          }
+          float V = 0.f;
+          for (int s = 0; s < S; ++s) { const float dz = sc[4 * 128 + pb + s] - D; V = fmaf(occ_[s] * T_[s], dz * dz, V); }
+          if (a.r_depth) a.r_depth[(size_t)b * R + ray] = D;
+          if (a.r_var) a.r_var[(size_t)b * R + ray] = V;
+          if (a.r_opacity) a.r_opacity[(size_t)b * R + ray] = O;
+          if (a.r_colour) { float* rc = a.r_colour + ((size_t)b * R + ray) * 3; rc[0] = C0; rc[1] = C1; rc[2] = C2; }
+          const float m_o = (sv != 0) ? 1.f : 0.f, m_s = (sv != 2) ? 1.f : 0.f, m_d = (mv != 0) ? m_o : 0.f;
+          const float info = 1.f / (sqrtf(V) + 1e-4f);
+          const float e_d = D - gd, e_o = O - m_o, e_c0 = C0 - gc0, e_c1 = C1 - gc1, e_c2 = C2 - gc2;
+          ls_d += on_d * fabsf(e_d) * m_d * info * inv_nd;
+          ls_c += on_c * (fabsf(e_c0) + fabsf(e_c1) + fabsf(e_c2)) * m_o * inv_no;
+          ls_o += on_o * fabsf(e_o) * m_s * inv_ns;
+          if (a.backward) {
+            const float gD = LS * on_d * vmb_sign(e_d) * m_d * info * inv_nd;
+            const float kc = LS * on_c * a.cs * m_o * inv_no;
+            const float gC0 = kc * vmb_sign(e_c0), gC1 = kc * vmb_sign(e_c1), gC2 = kc * vmb_sign(e_c2);
+            const float gO = LS * on_o * a.os * vmb_sign(e_o) * m_s * inv_ns;
+            float suffix = 0.f;
+            for (int s = S - 1; s >= 0; --s) {
+              const int q = pb + s;
+              const float occ = occ_[s], Ts = T_[s], w = occ * Ts;
+              const float c0 = sc[1 * 128 + q], c1 = sc[2 * 128 + q], c2 = sc[3 * 128 + q];
+              const float Gs = fmaf(gD, sc[4 * 128 + q], fmaf(gC0, c0, fmaf(gC1, c1, fmaf(gC2, c2, gO))));
+              const float docc = Gs * Ts - suffix / (1.f - occ + 1e-10f);
+              const float da = clamp_h(10.0f * docc * occ * (1.f - occ));
+              const float d0 = clamp_h(gC0 * w * c0 * (1.f - c0)), d1 = clamp_h(gC1 * w * c1 * (1.f - c1));
+              const float d2 = clamp_h(gC2 * w * c2 * (1.f - c2));
+              *reinterpret_cast<uint2*>(act + FG_DH * FGB + q * 16) = make_uint2(pack_h2(da, d0), pack_h2(d1, d2));
+              suffix = fmaf(Gs, w, suffix);
+            }
+          }
+        }
+        if (!a.backward) { group_bar(g); continue; }
+
+        STAGE_SYNC();                               // st6: d_hc (+ wgrad heads)
+        EPI_DGRAD(tA, FG_HC, mc);
+        STAGE_SYNC();                               // st7: d_fc4, d_emb2 (+ wgrad color_linear)
+        EPI_DGRAD(tB, FG_FC4, m4);
+        uint32_t ge2[21];                           // (g_k4, g_k5) per direction, packed fp16
+        {
+          float v[32];
+          ptx::tmem_ld32(tE, v);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int d = 0; d < 16; ++d) ge2[d] = pack_h2(clamp_h(v[2 * d]), clamp_h(v[2 * d + 1]));
+          float u[16];
+          ptx::tmem_ld16(tE + 32, u);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int d = 16; d < 21; ++d) ge2[d] = pack_h2(clamp_h(u[2 * (d - 16)]), clamp_h(u[2 * (d - 16) + 1]));
+        }
+        STAGE_SYNC();                               // st8: d_fc3 (+ wgrad mid2)
+        EPI_DGRAD(tA, FG_FC3, m3);
+        STAGE_SYNC();                               // st9: d_fc2, d_emb1 part 1 (+ wgrad cat_layer)
+        EPI_DGRAD(tB, FG_FC2, m2);
+        STAGE_SYNC();                               // st10: d_fc1 (+ wgrad mid1)
+        EPI_DGRAD(tA, FG_FC1, m1);
+        STAGE_SYNC();                               // st11: d_emb1 part 2 (+ wgrad in_layer)
+        // ---- PE backward: dproj_d = pi * sum_k 2^k g_{k,d} cos(pi 2^k proj_d); dB += dproj^T t
+        {
+          const float* Bd = wf + F_DIRS;
+          float v[32];
+#pragma unroll
+          for (int blk = 0; blk < 3; ++blk) {
+            ptx::tmem_ld32(tE + blk * 32, v);
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              // 4 columns per direction; block 0 starts with [1, x, y, z] then direction 20
+              int d;
+              if (blk == 0 && e == 0) continue;
+              if (blk == 0 && e == 1) d = 20; else d = 2 * (blk * 4 + (e >> 1) - 1) + (e & 1);
+              if (d > 19 && !(blk == 0 && e == 1)) continue;
+              float s[6], c[6];
+              sincos_ladder(fmaf(Bd[d * 3 + 2], t2x, fmaf(Bd[d * 3 + 1], t1x, Bd[d * 3] * t0x)), s, c);
+              const __half2 h45 = *reinterpret_cast<const __half2*>(&ge2[d]);
+              float dp = v[e * 4] * c[0];
+              dp = fmaf(2.f * v[e * 4 + 1], c[1], dp);
+              dp = fmaf(4.f * v[e * 4 + 2], c[2], dp);
+              dp = fmaf(8.f * v[e * 4 + 3], c[3], dp);
+              dp = fmaf(16.f * __low2float(h45), c[4], dp);
+              dp = fmaf(32.f * __high2float(h45), c[5], dp);
+              dp *= VMB_PI_F;
+              dBacc[d * 3 + 0] = fmaf(dp, t0x, dBacc[d * 3 + 0]);
+              dBacc[d * 3 + 1] = fmaf(dp, t1x, dBacc[d * 3 + 1]);
+              dBacc[d * 3 + 2] = fmaf(dp, t2x, dBacc[d * 3 + 2]);
+            }
+          }
+        }
+        ptx::tc_fence_before();
+        group_bar(g);                               // everyone is done with sc / TMEM before the next tile
+        ptx::tc_fence_after();
+      }
+#undef STAGE_SYNC
+#undef EPI_RELU
+#undef EPI_DGRAD
+      // ---- per-(CTA, object) flush of the register-resident partial sums ----------------
+      ls_d = warp_sum(ls_d); ls_c = warp_sum(ls_c); ls_o = warp_sum(ls_o);
+      if ((tid & 31) == 0 && a.loss_terms) {
+        atomicAdd(a.loss_terms + b * 4 + 0, ls_d); atomicAdd(a.loss_terms + b * 4 + 1, ls_c);
+        atomicAdd(a.loss_terms + b * 4 + 2, ls_o);
+        atomicAdd(a.loss_terms + b * 4 + 3, ls_d + a.cs * ls_c + a.os * ls_o);
+      }
+      if (a.backward) {
+        float* G = a.grads + (size_t)b * L.stride + L.o_B;
+#pragma unroll
+        for (int i = 0; i < 63; ++i) {
+          const float s = warp_sum(dBacc[i]);
+          if ((tid & 31) == 0) atomicAdd(G + i, s * INV_LS);
+        }
+      }
+    }
+
+    // ---- segment end: all MMAs have completed (each group waited on its last commit) -----
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    if (a.backward && warp < 8) {
+      // flush the wgrad accumulators: TMEM -> registers -> fp32 atomics on the grad block
+      float* G = a.grads + (size_t)b * L.stride;
+      const int q = warp & 3, half = warp >> 2, lane = q * 32 + (tid & 31);
+#pragma unroll 1
+      for (int cc = 0; cc < 3; ++cc) {
+        const int blk = half * 3 + cc;
+        float v[32];
+        ptx::tmem_ld32(tm + ((uint32_t)(q * 32) << 16) + blk * 32, v);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int idx = wg_target(L, blk, lane, j);
+          if (idx >= 0) atomicAdd(G + idx, v[j] * INV_LS);
+        }
+      }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+  }
+
+  if (warp == 8) ptx::tmem_dealloc(tm, 512);
+}
+
+// ---------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------
+static int umma_image_bytes() { return um::IMG_BYTES; }
+
+// param index -> location in the image: t >= 0 half index; t <= -2 float word index -(t+2); -1 none
+static void umma_fill_image_index(const VmbLayout& L, int* idx) {
+  using namespace um;
+  for (int i = 0; i < L.P; ++i) idx[i] = -1;
+  auto fslot = [](int f) { return -(IMG_F32 / 4 + f) - 2; };
+  const int H = 32;
+  for (int o = 0; o < H; ++o) {
+    for (int j = 0; j < VMB_E1; ++j) idx[L.o_Win + o * VMB_E1 + j] = widx32(IMG_WIN, o, j_to_emb1_col(j));
+    idx[L.o_bin + o] = fslot(F_BIN + o);
+    for (int k = 0; k < H; ++k) idx[L.o_Wm1 + o * H + k] = widx32(IMG_WM1, o, k);
+    idx[L.o_bm1 + o] = fslot(F_BM1 + o);
+    for (int k = 0; k < H + VMB_E1; ++k)
+      idx[L.o_Wcat + o * (H + VMB_E1) + k] = widx32(IMG_WCAT, o, k < H ? k : H + j_to_emb1_col(k - H));
+    idx[L.o_bcat + o] = fslot(F_BCAT + o);
+    for (int k = 0; k < H; ++k) idx[L.o_Wm2 + o * H + k] = widx32(IMG_WM2, o, k);
+    idx[L.o_bm2 + o] = fslot(F_BM2 + o);
+    for (int k = 0; k < H + L.e2; ++k)
+      idx[L.o_Wcl + o * (H + L.e2) + k] = widx32(IMG_WCL, o, k < H ? k : H + j2_to_emb2_col(k - H));
+    idx[L.o_bcl + o] = fslot(F_BCL + o);
+    idx[L.o_Wa + o] = widx16(IMG_WA16, 0, o);
+    for (int c = 0; c < 3; ++c) idx[L.o_Woc + c * H + o] = widx16(IMG_WOC16, 1 + c, o);
+  }
+  idx[L.o_ba] = fslot(F_BA);
+  for (int c = 0; c < 3; ++c) idx[L.o_boc + c] = fslot(F_BOC + c);
+  for (int i = 0; i < VMB_NDIRS * 3; ++i) idx[L.o_B + i] = fslot(F_DIRS + i);
+}
+
+static int umma_launch_step(const VmbLayout& L, const StepParams& sp, const void* image, cudaStream_t st, std::string& err) {
+  using namespace um;
+  if (L.H != 32 || L.nfreq != 6) { err = "UMMA step kernel: hidden must be 32 and n_freq 6"; return -4; }
+  if (sp.S > UMMA_MAX_S) { err = "UMMA step kernel: n_samples > 16"; return -4; }
+  static int n_sm = 0;
+  if (n_sm == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    cudaError_t e = cudaFuncSetAttribute(k_step_umma, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e != cudaSuccess) { n_sm = 0; err = std::string("cudaFuncSetAttribute(k_step_umma): ") + cudaGetErrorString(e); return -2; }
+  }
+  const int nr = 128 / sp.S;
+  const int tpo = (sp.R + nr - 1) / nr;
+  const long long T = (long long)tpo * sp.B;
+  long long grid = (T + 1) / 2;
+  if (grid > n_sm) grid = n_sm;
+  if (grid < 1) grid = 1;
+  k_step_umma<<<(unsigned)grid, NT, SMEM_BYTES, st>>>(sp, L, (const unsigned char*)image, tpo, nr, T);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { err = std::string("k_step_umma launch: ") + cudaGetErrorString(e); return -2; }
+  return 0;
 }
