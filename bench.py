@@ -1,0 +1,270 @@
+#!/usr/bin/env python
+"""Benchmark of the vMAP vectorised per-object training step (BASELINE.json metric:
+training-step rays/s at n_obj x n_rays x n_samples).
+
+    python bench.py --gpus N --steps K --warmup W            # this framework on N GPUs
+    python bench.py --impl reference --steps K --warmup W    # CPU reference arm (oracle port)
+
+A "step" is one optimisation step of train.py:293-326 for the whole stack of objects:
+mask counts + fused PE/MLP/render/loss/backward (K0+K1) + fused AdamW (K2).
+N=1 workload = BASELINE cfg 2 (20 objects x 1200 rays x 10 samples, hidden 32).
+N>1 = cfg 4, weak scaling: 20 objects per GPU, objects sharded across ranks, no
+collective in the step (per-GPU independent Adam) -- only the timing barrier.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_OBJ, N_RAYS, N_SAMPLES, HIDDEN = 20, 1200, 10, 32
+FLOP_PER_POINT = 6 * (4 * HIDDEN * HIDDEN + 220 * HIDDEN + 63)      # 67,194 @ H=32
+METRIC = "training-step rays/sec at n_obj x n_rays x n_samples"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        d = json.load(open(p))
+        return d.get("bf16_tflops", 1590.0), d.get("bf16_tflops_sustained", 1400.0), d.get("hbm_gbs", 6650.0), "measured"
+    return 1590.0, 1400.0, 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.lines, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for ln in self.proc.stdout:
+            self.lines.append((time.time(), ln.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.12)
+        self.proc.terminate()
+        rows = [l for (t, l) in self.lines if t0 - 0.05 <= t <= t1 + 0.05] or [l for _, l in self.lines]
+        sm, mx, reasons = [], None, set()
+        for l in rows:
+            f = [x.strip() for x in l.split(",")]
+            try:
+                sm.append(float(f[0])); mx = float(f[1])
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_reference_rate(steps, warmup, bounded=True):
+    """Times the CPU oracle port (oracle/vmap_oracle.py: the reference's functorch step
+    restated op for op) with every host thread.  Returns (rays/s, ms/step, cores, sample)."""
+    import torch
+    from oracle import vmap_oracle as vo
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    rays = N_RAYS
+    if bounded and steps * 0.5 > 120.0:          # keep the whole run within a few minutes
+        rays = max(60, int(N_RAYS * 120.0 / (steps * 0.5)) // 12 * 12)
+    params = vo.init_params(N_OBJ, HIDDEN, seed=0)
+    ens = vo.OracleEnsemble(params, 2.0)
+    batches = [vo.synthetic_batch(N_OBJ, rays, N_SAMPLES, seed=i) for i in range(2)]
+    for i in range(warmup):
+        ens.step(batches[i % 2])
+    t0 = time.perf_counter()
+    for i in range(steps):
+        ens.step(batches[i % 2])
+    dt = time.perf_counter() - t0
+    sample = f"{steps} full optimisation steps of {N_OBJ} obj x {rays} rays x {N_SAMPLES} samples, fp32, {cores} threads"
+    return N_OBJ * rays * steps / dt, dt / steps * 1e3, cores, sample
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    rate, ms, cores, sample = cpu_reference_rate(args.steps, args.warmup)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": "rays/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"vMAP {N_OBJ} objects x {N_RAYS} rays x {N_SAMPLES} samples, hidden {HIDDEN} (BASELINE cfg 2)",
+                   "note": "reference is pure Python/PyTorch and cannot travel to the GPU box; this arm times the CPU port "
+                           "of its functorch step (oracle/vmap_oracle.py), validated against the reference's own modules"},
+        "cpu_baseline": {"value": rate, "unit": "rays/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": rate, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from oracle import vmap_oracle as vo          # input generator + cpu_baseline leg only
+    from vmap_b200.ensemble import VmapEnsemble
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback for the vMAP step)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    impl = os.environ.get("VMB_IMPL", "auto")
+
+    B, R, S = N_OBJ, N_RAYS, N_SAMPLES            # per GPU (weak scaling)
+    params = vo.init_params(B, HIDDEN, seed=1000 + rank)
+    ens = VmapEnsemble(B, hidden=HIDDEN, scale=2.0, device=dev, impl=impl)
+    ens.load_stacked(params)
+
+    # input pool larger than L2 (126 MB): every step reads a different, cold batch
+    step_bytes = B * R * S * 16 + B * R * 18
+    n_pool = max(8, int(140e6 // step_bytes) + 1)
+    host_pool, dev_pool = [], []
+    for i in range(n_pool):
+        hb = vo.synthetic_batch(B, R, S, seed=rank * 100003 + i)
+        hb["mask_depth"] = hb["mask_depth"].to(torch.uint8)
+        host_pool.append({k: v.pin_memory() for k, v in hb.items()})
+    for i in range(n_pool):
+        dev_pool.append({k: v.to(dev) for k, v in host_pool[i].items()})
+    stage = [{k: torch.empty_like(v, device=dev) for k, v in host_pool[0].items()} for _ in range(2)]
+    loss_host = torch.zeros(1, dtype=torch.float32).pin_memory()
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return ms
+
+    K, W = args.steps, max(args.warmup, 3)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+
+    # ---- device-resident arm ("value") ----------------------------------------------------
+    for i in range(W):
+        ens.step(dev_pool[i % n_pool])
+    barrier()
+    k1_events = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall0 = time.time()
+    e0.record()
+    for i in range(K):
+        ens.forward_backward(dev_pool[(W + i) % n_pool], k1_events=k1_events[i])
+        ens.adam_step()
+    e1.record()
+    barrier()
+    t_wall1 = time.time()
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    k1_ms = sorted(a.elapsed_time(b) for a, b in k1_events)
+    k1_avg_ms = sum(k1_ms) / len(k1_ms)
+    ens.check_status()
+    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
+
+    # ---- end-to-end arm: pinned host inputs -> H2D -> step -> D2H loss ---------------------
+    for i in range(3):
+        sb = stage[i % 2]
+        for k, v in host_pool[i % n_pool].items():
+            sb[k].copy_(v, non_blocking=True)
+        loss_host.copy_(ens.step(sb).reshape(1), non_blocking=True)
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for i in range(K):
+        sb = stage[i % 2]
+        for k, v in host_pool[(i + 3) % n_pool].items():
+            sb[k].copy_(v, non_blocking=True)
+        loss_host.copy_(ens.step(sb).reshape(1), non_blocking=True)
+    f1.record()
+    barrier()
+    e2e_ms = max_over_ranks(f0.elapsed_time(f1))
+    ens.check_status()
+
+    if rank == 0:
+        bf16_burst, bf16_sust, hbm, src = peaks()
+        rays_total = world * B * R * K
+        flop_k1 = FLOP_PER_POINT * B * R * S
+        achieved = flop_k1 / (k1_avg_ms * 1e-3) / 1e12
+        line = {
+            "metric": METRIC, "value": rays_total / (ms_total * 1e-3), "unit": "rays/s", "n_gpus": world,
+            "steps": K, "warmup": W, "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "fp16", "data": "synthetic",
+            "config": {
+                "workload": f"vMAP {B} objects/GPU x {R} rays x {S} samples, hidden {HIDDEN} "
+                            f"(BASELINE cfg {'2' if world == 1 else '4: objects sharded ' + str(B) + '/GPU'})",
+                "global_objects": world * B, "parallelism": f"object-sharded x{world}, no collective in the step",
+                "precision": "fp16 tensor-core operands, fp32 accumulate, fp32 master weights / Adam / render / loss",
+                "impl": impl, "l2": f"input pool of {n_pool} distinct batches ({n_pool * step_bytes / 1e6:.0f} MB > 126 MB L2)",
+                "d2h": "loss scalar copied to pinned host memory every step (async), one sync at the end",
+            },
+            "e2e": {"value": rays_total / (e2e_ms * 1e-3), "unit": "rays/s", "ms_per_step": e2e_ms / K,
+                    "h2d_bytes_per_step": step_bytes, "d2h_bytes_per_step": 4},
+            "gpu_launches": 3 * K,
+            "roofline": {"bound": "tensor", "achieved": achieved, "peak": bf16_burst, "unit": "TFLOP/s",
+                         "frac": achieved / bf16_burst, "traffic": None, "peak_source": src + " bf16 burst",
+                         "peak_sustained": bf16_sust, "kernel": "k_step_umma" if impl in ("auto", "umma") else "k_step_fp32",
+                         "kernel_us": k1_avg_ms * 1e3, "kernel_us_median": k1_ms[len(k1_ms) // 2] * 1e3,
+                         "flop_per_launch": flop_k1,
+                         "hbm_algorithmic_GBps": (B * R * S * 16 + B * R * 18) / (k1_avg_ms * 1e-3) / 1e9, "hbm_peak": hbm},
+            "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu:
+            n_cpu = 12
+            rate, ms, cores, sample = cpu_reference_rate(n_cpu, 2, bounded=False)
+            line["cpu_baseline"] = {"value": rate, "unit": "rays/s", "cores": cores, "kind": "port",
+                                    "ms_per_step": ms, "sample": sample}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

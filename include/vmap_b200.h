@@ -103,6 +103,8 @@ typedef struct vmb_step_args {
   float opacity_scaling;            /* 10.0 (loss.py:6)                                    */
   int   backward;                   /* 1 = forward+backward, 0 = forward/loss only         */
   int   reserved;
+  void* k1_start_event;             /* optional cudaEvent_t recorded right before / after   */
+  void* k1_stop_event;              /*   the fused K1 launch (roofline timing in bench.py)  */
 } vmb_step_args;
 
 int vmb_step(vmb_handle* h, const vmb_step_args* a, void* stream);

@@ -37,6 +37,7 @@ class StepArgs(C.Structure):
         ("counts", _vp),
         ("colour_scaling", C.c_float), ("opacity_scaling", C.c_float),
         ("backward", C.c_int), ("reserved", C.c_int),
+        ("k1_start_event", _vp), ("k1_stop_event", _vp),
     ]
 
 

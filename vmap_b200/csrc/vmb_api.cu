@@ -171,6 +171,11 @@ int vmb_step(vmb_handle* h, const vmb_step_args* a, void* stream) {
   sp.params = a->params; sp.scale = a->scale; sp.grads = a->grads; sp.loss_terms = a->loss_terms;
   sp.r_depth = a->r_depth; sp.r_var = a->r_var; sp.r_colour = a->r_colour; sp.r_opacity = a->r_opacity;
   sp.counts = counts; sp.cs = a->colour_scaling; sp.os = a->opacity_scaling; sp.backward = a->backward;
+  struct EvGuard {      // records the optional K1 timing events around whichever kernel runs
+    cudaEvent_t stop; cudaStream_t st;
+    ~EvGuard() { if (stop) cudaEventRecord(stop, st); }
+  } evg{(cudaEvent_t)a->k1_stop_event, st};
+  if (a->k1_start_event) cudaEventRecord((cudaEvent_t)a->k1_start_event, st);
   if (impl == VMB_IMPL_UMMA) {
     if (!umma_possible) return fail(h, VMB_E_UNSUPPORTED, "vmb_step: UMMA path needs hidden=32, n_freq=6, an image and S<=16");
     std::string err;

@@ -136,9 +136,16 @@ class VmapEnsemble:
         return a
 
     def forward_backward(self, batch, outputs=None, backward: bool = True, impl: Optional[str] = None,
-                         counts: Optional[torch.Tensor] = None):
-        """K0 + K1: accumulates into ``self.grads`` and overwrites ``self.loss_terms``."""
+                         counts: Optional[torch.Tensor] = None, k1_events=None):
+        """K0 + K1: accumulates into ``self.grads`` and overwrites ``self.loss_terms``.
+        ``k1_events`` = (start, stop) torch.cuda.Event pair recorded around the K1 launch."""
         a = self._step_args(batch, backward, outputs, impl, counts)
+        if k1_events is not None:
+            for ev in k1_events:
+                if not ev.cuda_event:
+                    ev.record()                  # torch creates the CUDA event lazily
+            a.k1_start_event = C.c_void_p(k1_events[0].cuda_event)
+            a.k1_stop_event = C.c_void_p(k1_events[1].cuda_event)
         with torch.cuda.device(self.device):
             _lib.check(self._handle, self.lib.vmb_step(self._handle, C.byref(a), _stream()), "vmb_step")
 
