@@ -85,21 +85,35 @@ def cpu_reference_rate(steps, warmup, bounded=True):
     restated op for op) with every host thread.  Returns (rays/s, ms/step, cores, sample)."""
     import torch
     from oracle import vmap_oracle as vo
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
+    total = os.cpu_count() or 1
     rays = N_RAYS
     if bounded and steps * 0.5 > 120.0:          # keep the whole run within a few minutes
         rays = max(60, int(N_RAYS * 120.0 / (steps * 0.5)) // 12 * 12)
     params = vo.init_params(N_OBJ, HIDDEN, seed=0)
     ens = vo.OracleEnsemble(params, 2.0)
     batches = [vo.synthetic_batch(N_OBJ, rays, N_SAMPLES, seed=i) for i in range(2)]
+    # "all the host threads it can use": these small batched GEMMs get SLOWER when oversubscribed,
+    # so pick the fastest thread count on this box (one step each) and report it.
+    best, cores = None, total
+    for n in sorted({total, max(1, total // 2), 64, 32, 16, 8}, reverse=True):
+        if n > total:
+            continue
+        torch.set_num_threads(n)
+        ens.step(batches[0])
+        t = time.perf_counter()
+        ens.step(batches[1])
+        t = time.perf_counter() - t
+        if best is None or t < best:
+            best, cores = t, n
+    torch.set_num_threads(cores)
     for i in range(warmup):
         ens.step(batches[i % 2])
     t0 = time.perf_counter()
     for i in range(steps):
         ens.step(batches[i % 2])
     dt = time.perf_counter() - t0
-    sample = f"{steps} full optimisation steps of {N_OBJ} obj x {rays} rays x {N_SAMPLES} samples, fp32, {cores} threads"
+    sample = (f"{steps} full optimisation steps of {N_OBJ} obj x {rays} rays x {N_SAMPLES} samples, fp32, "
+              f"{cores} threads (fastest of the thread counts tried on a {total}-core host)")
     return N_OBJ * rays * steps / dt, dt / steps * 1e3, cores, sample
 
 

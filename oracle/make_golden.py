@@ -152,8 +152,24 @@ def reference_sampler_case(name, seed, n_kf, n_frames, n_samples, n1, W=64, H=48
     print(name, "pcs", tuple(o_pcs.shape), "valid", int(o_valid.sum()))
 
 
+def reference_config_case():
+    """Attribute bag of the reference's Config for the two shipped Replica room0 files."""
+    import json
+    cfg_mod = _refload.load("cfg")
+    out = {}
+    for tag, rel in (("vMAP", "configs/Replica/config_replica_room0_vMAP.json"),
+                     ("iMAP", "configs/Replica/config_replica_room0_iMAP.json")):
+        path = os.path.join(_refload.REF_ROOT, rel)
+        c = cfg_mod.Config(path)
+        attrs = {k: (v.tolist() if hasattr(v, "tolist") else v) for k, v in vars(c).items()}
+        out[tag] = {"raw": json.load(open(path)), "attrs": attrs}
+    json.dump(out, open(os.path.join(OUT, "config_room0.json"), "w"), indent=1, sort_keys=True)
+    print("config_room0", sorted(out["vMAP"]["attrs"])[:5], "...")
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    reference_config_case()
     # vMAP object ensemble (room0_vMAP.json: H=32, scale 2, 1+9 samples), 3 AdamW steps
     reference_step_case("step_vmap_h32", n_obj=3, hidden=32, n_rays=24, n_samples=10, scale=2.0,
                         n_cam2surf=1, seed=1, n_steps=3)

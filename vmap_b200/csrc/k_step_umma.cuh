@@ -2,9 +2,11 @@
 // fp16 operands / fp32 accumulate on the 5th-gen tensor cores (tcgen05.mma, TMEM
 // accumulators), weights staged per object with one bulk async copy (TMA engine).
 //
-// CTA = 288 threads: two "point groups" of 128 threads (one thread = one sample point =
-// one TMEM lane) plus one MMA-issuer warp.  Each group walks its tile (up to 128 points =
-// whole rays) through 12 MMA stages in lock-step: threads write the next operand rows to
+// CTA = 544 threads: two "point groups" of 256 threads plus one MMA-issuer warp.  A group owns
+// a tile of up to 128 sample points (whole rays); two threads share a point (= one TMEM lane),
+// splitting the accumulator columns / PE directions, so the per-stage epilogue latency halves
+// and each SM sub-partition has 4 resident compute warps.  Each group walks its tile through
+// 12 MMA stages in lock-step: threads write the next operand rows to
 // shared memory, arrive on the group's request mbarrier, the issuer thread issues the
 // stage's tcgen05.mma batch and commits to the group's done mbarrier, threads read the
 // accumulator back with tcgen05.ld.  The two groups run out of phase, so one group's
@@ -36,7 +38,8 @@
 
 namespace um {
 
-constexpr int NT = 288;
+constexpr int GT = 256;                  // threads per point group
+constexpr int NT = 2 * GT + 32;           // + the MMA issuer warp
 constexpr int FGB = 2048;                 // bytes of one 8-feature group for 128 points
 // feature-group index of each block inside a group's activation region
 constexpr int FG_HC = 0, FG_DH = 4, FG_FC1 = 6, FG_FC2 = 10, FG_E1 = 14, FG_FC3 = 26, FG_FC4 = 30, FG_E2 = 34;
@@ -49,10 +52,13 @@ constexpr int IMG_WA16 = 23552, IMG_WOC16 = 24576, IMG_F32 = 25600;
 constexpr int F_BIN = 0, F_BM1 = 32, F_BCAT = 64, F_BM2 = 96, F_BCL = 128, F_BA = 160, F_BOC = 161, F_DIRS = 168;
 constexpr int IMG_BYTES = 26624;
 // shared memory map
-constexpr int SM_ACT0 = 0, SM_ACT1 = ACT_BYTES, SM_W = 2 * ACT_BYTES, SM_SC = SM_W + IMG_BYTES;
-constexpr int SC_BYTES = 5 * 128 * 4;                     // alpha, c0, c1, c2, z per point
-constexpr int SM_MISC = SM_SC + 2 * SC_BYTES;
-constexpr int SMEM_BYTES = SM_MISC + 256;
+constexpr int SM_ACT0 = 0, SM_ACT1 = ACT_BYTES, SM_W = 2 * ACT_BYTES, SM_G = SM_W + IMG_BYTES;
+// per-group fp32 scratch: 12 rows of 128 floats, per-ray broadcast slots, dB accumulators, dproj
+constexpr int R_OCC = 0, R_F = 1, R_C0 = 2, R_C1 = 3, R_C2 = 4, R_Z = 5, R_W = 6, R_T = 7, R_GW = 8, R_T0 = 9, R_T1 = 10, R_T2 = 11;
+constexpr int GS_RB = 12 * 512, GS_DBS = GS_RB + 5 * 512, GS_DPR = GS_DBS + 256;   // rb = [5][128] per-ray gradients
+constexpr int GS_BYTES = GS_DPR + 21 * 512;               // 19712
+constexpr int SM_MISC = SM_G + 2 * GS_BYTES;
+constexpr int SMEM_BYTES = SM_MISC + 256;                 // 230144 <= 227 KB (232448)
 // TMEM columns
 constexpr int WG_IN = 0, WG_M1 = 32, WG_CAT = 64, WG_M2 = 96, WG_CL = 128, WG_A = 160, WG_OC = 176;
 constexpr int ACC0 = 192, ACC_STRIDE = 160;               // per group: A[0,32) B[32,64) E[64,160)
@@ -128,11 +134,28 @@ __device__ __forceinline__ int wg_target(const VmbLayout& L, int blk, int lane, 
   }
 }
 
-__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
-  __half2 h = __floats2half2_rn(a, b);
+// two floats -> packed fp16x2 (lo, hi), saturating to +-65504 instead of overflowing to inf
+__device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ uint32_t relu_h2(uint32_t x) {
+  __half2 h = __hmax2(*reinterpret_cast<__half2*>(&x), __float2half2_rn(0.f));
   return *reinterpret_cast<uint32_t*>(&h);
 }
-__device__ __forceinline__ float clamp_h(float x) { return fminf(fmaxf(x, -HMAX), HMAX); }
+// dy * (h > 0), packed
+__device__ __forceinline__ uint32_t gate_h2(uint32_t dy, uint32_t h) {
+  const __half2 m = __hgt2(*reinterpret_cast<__half2*>(&h), __float2half2_rn(0.f));
+  __half2 r = __hmul2(*reinterpret_cast<__half2*>(&dy), m);
+  return *reinterpret_cast<uint32_t*>(&r);
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr) : "memory");
+}
 
 __device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
@@ -152,7 +175,7 @@ __device__ __forceinline__ void mbar_wait_or_trap(uint64_t* bar, uint32_t parity
     if (ptx::mbar_try_wait(bar, parity)) return;
   __trap();
 }
-__device__ __forceinline__ void group_bar(int g) { asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory"); }
+__device__ __forceinline__ void group_bar(int g) { asm volatile("bar.sync %0, 256;" ::"r"(1 + g) : "memory"); }
 
 struct Misc {
   uint64_t req[2], done[2], wbar;
@@ -218,12 +241,10 @@ struct Issuer {
         wgrad(g, WG_OC, 6, FG_HC, FG_DH, MM16);
         wgrad(g, WG_A, 5, FG_FC4, FG_DH, MM16);
         break;
-      case 7:   // d_fc4 = dYc @ W_cl[:, :32] + dhead @ W_a -> B ; d_emb2 = dYc @ W_cl[:, 32:] -> E[0..48) ; wgrad color_linear
+      case 7:   // d_fc4 = dYc @ W_cl[:, :32] + dhead @ W_a -> B ; wgrad color_linear
 #pragma unroll
         for (int ks = 0; ks < 2; ++ks) ptx::umma_f16(B, a_k(g, FG_HC, ks), w_mn(IMG_WCL, ks), KM32, ks > 0);
         ptx::umma_f16(B, a_k(g, FG_DH, 0), w16_mn(IMG_WA16), KM32, 1u);
-#pragma unroll
-        for (int ks = 0; ks < 2; ++ks) ptx::umma_f16(E, a_k(g, FG_HC, ks), w_mn(IMG_WCL + 4 * 512, ks), KM48, ks > 0);
         wgrad(g, WG_CL, 4, FG_FC4, FG_HC, MM32);
         break;
       case 8:   // d_fc3 = dY4 @ W_m2 -> A ; wgrad mid2
@@ -243,25 +264,35 @@ struct Issuer {
         for (int ks = 0; ks < 2; ++ks) ptx::umma_f16(A, a_k(g, FG_FC2, ks), w_mn(IMG_WM1, ks), KM32, ks > 0);
         wgrad(g, WG_M1, 1, FG_FC1, FG_FC2, MM32);
         break;
-      default:  // 11: d_emb1 += dY1 @ W_in -> E ; wgrad in_layer
+      default:  // 11: d_emb1 += dY1 @ W_in -> E ; d_emb2 = dYc @ W_cl[:, 32:] -> A[0..48) (dYc still sits in the hc block) ; wgrad in_layer
 #pragma unroll
         for (int ks = 0; ks < 2; ++ks) ptx::umma_f16(E, a_k(g, FG_FC1, ks), w_mn(IMG_WIN, ks), KM96, 1u);
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) ptx::umma_f16(A, a_k(g, FG_HC, ks), w_mn(IMG_WCL + 4 * 512, ks), KM48, ks > 0);
         wgrad(g, WG_IN, 0, FG_E1, FG_FC1, MM32);
         break;
     }
   }
 };
 
-// per-direction sin/cos ladder: s[k] = sin(pi 2^k proj), c[k] = cos(...), k = 0..5
-__device__ __forceinline__ void sincos_ladder(float proj, float (&s)[6], float (&c)[6]) {
+// sin(pi 2^k x), k = 0..5: one MUFU sin/cos pair, then angle doubling
+__device__ __forceinline__ void sin_ladder(float proj, float (&s)[6]) {
   const float r = proj - 2.0f * rintf(0.5f * proj);          // exact: sin(pi x) has period 2
   s[0] = __sinf(VMB_PI_F * r);
-  c[0] = __cosf(VMB_PI_F * r);
+  float c = __cosf(VMB_PI_F * r);
 #pragma unroll
   for (int k = 1; k < 6; ++k) {
-    s[k] = 2.0f * s[k - 1] * c[k - 1];
-    c[k] = fmaf(-2.0f * s[k - 1], s[k - 1], 1.0f);
+    const float s2 = s[k - 1] + s[k - 1];
+    s[k] = s2 * c;
+    c = fmaf(-s2, s[k - 1], 1.0f);
   }
+}
+// cos(pi 2^k x), k = 0..5
+__device__ __forceinline__ void cos_ladder(float proj, float (&c)[6]) {
+  const float r = proj - 2.0f * rintf(0.5f * proj);
+  c[0] = __cosf(VMB_PI_F * r);
+#pragma unroll
+  for (int k = 1; k < 6; ++k) c[k] = fmaf(c[k - 1] + c[k - 1], c[k - 1], -1.0f);
 }
 
 }  // namespace um
@@ -276,13 +307,13 @@ k_step_umma(StepParams a, VmbLayout L, const unsigned char* __restrict__ image, 
   const int S = a.S, R = a.R;
 
   if (tid == 0) {
-    ptx::mbar_init(&misc->req[0], 128); ptx::mbar_init(&misc->req[1], 128);
+    ptx::mbar_init(&misc->req[0], GT); ptx::mbar_init(&misc->req[1], GT);
     ptx::mbar_init(&misc->done[0], 1);  ptx::mbar_init(&misc->done[1], 1);
     ptx::mbar_init(&misc->wbar, 1);
     misc->abort_flag = 0;
     ptx::mbar_init_fence();
   }
-  if (warp == 8) { ptx::tmem_alloc(&misc->tmem_base, 512); ptx::tmem_relinquish(); }
+  if (warp == 16) { ptx::tmem_alloc(&misc->tmem_base, 512); ptx::tmem_relinquish(); }
   if (tid < 3) {                      // render_rays.py:68-73: one empty mask anywhere zeroes the term for all
     int on = 1;
     for (int i = 0; i < a.B; ++i) on &= (a.counts[i * 4 + tid] != 0);
@@ -314,9 +345,9 @@ k_step_umma(StepParams a, VmbLayout L, const unsigned char* __restrict__ image, 
     mbar_wait_or_trap(&misc->wbar, wpar);
     wpar ^= 1;
 
-    if (warp == 8) {
+    if (warp == 16) {
       // =========================== MMA issuer ===========================================
-      if (tid == 256) {
+      if (tid == 2 * GT) {
         Issuer is;
         is.act[0] = ptx::smem_u32(smem + SM_ACT0); is.act[1] = ptx::smem_u32(smem + SM_ACT1);
         is.W = ptx::smem_u32(smem + SM_W); is.tm = tm; is.wg_started = 0;
@@ -340,21 +371,27 @@ k_step_umma(StepParams a, VmbLayout L, const unsigned char* __restrict__ image, 
       }
     } else {
       // =========================== point groups ==========================================
-      const int g = warp >> 2, tg = tid & 127;
+      const int g = warp >> 3, tg = tid & (GT - 1);
+      const int p = tg & 127, hsel = tg >> 7;          // point slot (= TMEM lane), column / direction half
       unsigned char* act = smem + (g ? SM_ACT1 : SM_ACT0);
-      float* sc = reinterpret_cast<float*>(smem + SM_SC + g * SC_BYTES);      // [5][128]
+      float* sc = reinterpret_cast<float*>(smem + SM_G + g * GS_BYTES);          // [12][128]
+      float* rb = reinterpret_cast<float*>(smem + SM_G + g * GS_BYTES + GS_RB);  // [5][128]
+      float* dbs = reinterpret_cast<float*>(smem + SM_G + g * GS_BYTES + GS_DBS);
+      float* dpr = reinterpret_cast<float*>(smem + SM_G + g * GS_BYTES + GS_DPR);  // [21][128]
       const float* wf = reinterpret_cast<const float*>(smem + SM_W + IMG_F32);
+      const float* Bd = wf + F_DIRS;
       const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
       const uint32_t tA = tm + ACC0 + g * ACC_STRIDE + lane_base, tB = tA + 32, tE = tA + 64;
-      const float scale_b = a.scale[b];
+      const float isc = 1.0f / a.scale[b];
       const float inv_nd = 1.f / ((float)a.counts[b * 4 + 0] + 1e-10f);
       const float inv_no = 1.f / ((float)a.counts[b * 4 + 1] + 1e-10f);
       const float inv_ns = 1.f / ((float)a.counts[b * 4 + 2] + 1e-10f);
       const float on_d = misc->on[0] ? 1.f : 0.f, on_c = misc->on[1] ? 1.f : 0.f, on_o = misc->on[2] ? 1.f : 0.f;
-      float dBacc[63];
-#pragma unroll
-      for (int i = 0; i < 63; ++i) dBacc[i] = 0.f;
       float ls_d = 0.f, ls_c = 0.f, ls_o = 0.f;
+      const int np = nr * S;
+      const int rl = p / S, sidx = p - rl * S;
+      if (tg < 64) dbs[tg] = 0.f;
+      group_bar(g);
 
 #define STAGE_SYNC()                                   \
   do {                                                 \
@@ -365,235 +402,252 @@ k_step_umma(StepParams a, VmbLayout L, const unsigned char* __restrict__ image, 
     ph ^= 1;                                           \
     ptx::tc_fence_after();                             \
   } while (0)
+      // hidden-layer epilogue on this thread's 16 columns: acc + bias -> ReLU -> fp16 (2 x 16 B)
+#define EPI_RELU(TADDR, BIAS_OFF, FG)                                                          \
+  do {                                                                                         \
+    float v[16];                                                                               \
+    ptx::tmem_ld16((TADDR) + 16 * hsel, v);                                                    \
+    ptx::tmem_ld_wait();                                                                       \
+    const float4* bp = reinterpret_cast<const float4*>(wf + (BIAS_OFF) + 16 * hsel);           \
+    uint32_t h[8];                                                                             \
+    _Pragma("unroll") for (int q = 0; q < 4; ++q) {                                            \
+      const float4 bb = bp[q];                                                                 \
+      h[2 * q] = relu_h2(pack_h2(v[4 * q] + bb.x, v[4 * q + 1] + bb.y));                       \
+      h[2 * q + 1] = relu_h2(pack_h2(v[4 * q + 2] + bb.z, v[4 * q + 3] + bb.w));               \
+    }                                                                                          \
+    uint4* dst = reinterpret_cast<uint4*>(act + ((FG) + 2 * hsel) * FGB + p * 16);             \
+    dst[0] = make_uint4(h[0], h[1], h[2], h[3]);                                               \
+    dst[128] = make_uint4(h[4], h[5], h[6], h[7]);                                             \
+  } while (0)
+      // dgrad epilogue: dY = (h > 0) * acc, written over h (the stored fp16 activation is the mask)
+#define EPI_DGRAD(TADDR, FG)                                                                   \
+  do {                                                                                         \
+    float v[16];                                                                               \
+    ptx::tmem_ld16((TADDR) + 16 * hsel, v);                                                    \
+    uint4* dst = reinterpret_cast<uint4*>(act + ((FG) + 2 * hsel) * FGB + p * 16);             \
+    const uint4 o0 = dst[0], o1 = dst[128];                                                    \
+    ptx::tmem_ld_wait();                                                                       \
+    dst[0] = make_uint4(gate_h2(pack_h2(v[0], v[1]), o0.x), gate_h2(pack_h2(v[2], v[3]), o0.y),       \
+                        gate_h2(pack_h2(v[4], v[5]), o0.z), gate_h2(pack_h2(v[6], v[7]), o0.w));      \
+    dst[128] = make_uint4(gate_h2(pack_h2(v[8], v[9]), o1.x), gate_h2(pack_h2(v[10], v[11]), o1.y),   \
+                          gate_h2(pack_h2(v[12], v[13]), o1.z), gate_h2(pack_h2(v[14], v[15]), o1.w)); \
+  } while (0)
+
+      // prefetched inputs of the next tile (global-load latency overlaps the current tile)
+      float nx = 0.f, ny = 0.f, nz = 0.f, nzv = 0.f, n_gd = 0.f, n_c0 = 0.f, n_c1 = 0.f, n_c2 = 0.f;
+      int n_sm = 0;
+      auto prefetch = [&](int t) {
+        nx = ny = nz = nzv = 0.f; n_gd = n_c0 = n_c1 = n_c2 = 0.f; n_sm = 0;
+        if (t >= t1) return;
+        const int r0n = t * nr;
+        if (p < np && r0n + rl < R) {
+          const size_t pi = (size_t)(r0n + rl) * S + sidx;
+          const float* pp = a.pcs + (size_t)b * a.pcs_stride + pi * 3;
+          nx = pp[0]; ny = pp[1]; nz = pp[2];
+          if (hsel == 0) nzv = a.z[(size_t)b * a.z_stride + pi];
+        }
+        if (hsel == 1 && p < nr && r0n + p < R) {      // ray threads
+          const int ray = r0n + p;
+          n_gd = a.gt_depth[(size_t)b * a.gt_depth_stride + ray];
+          const float* gcp = a.gt_colour + (size_t)b * a.gt_colour_stride + (size_t)ray * 3;
+          n_c0 = gcp[0]; n_c1 = gcp[1]; n_c2 = gcp[2];
+          n_sm = (int)a.sem[(size_t)b * a.sem_stride + ray] | ((int)a.mask[(size_t)b * a.mask_stride + ray] << 8) | 0x10000;
+        }
+      };
+      prefetch(t0 + g);
 
       for (int t = t0 + g; t < t1; t += 2) {
         const int r0 = t * nr;
-        const int rl = tg / S, sidx = tg - rl * S;
-        const bool pvalid = (tg < nr * S) && (r0 + rl < R);
-        // ---- E0: load point + positional embedding ------------------------------------
-        float t0x = 0.f, t1x = 0.f, t2x = 0.f, zz = 0.f;
-        if (pvalid) {
-          const size_t pi = (size_t)(r0 + rl) * S + sidx;
-          const float* pp = a.pcs + (size_t)b * a.pcs_stride + pi * 3;
-          const float isc = 1.0f / scale_b;
-          t0x = pp[0] * isc; t1x = pp[1] * isc; t2x = pp[2] * isc;
-          zz = a.z[(size_t)b * a.z_stride + pi];
-        }
-        sc[4 * 128 + tg] = zz;
-        // ray-thread inputs, fetched early (consumed at the render stage)
-        const bool is_ray = (tg < nr) && (r0 + tg < R);
-        float gd = 0.f, gc0 = 0.f, gc1 = 0.f, gc2 = 0.f; int sv = 0, mv = 0;
-        if (is_ray) {
-          const int ray = r0 + tg;
-          gd = a.gt_depth[(size_t)b * a.gt_depth_stride + ray];
-          const float* gcp = a.gt_colour + (size_t)b * a.gt_colour_stride + (size_t)ray * 3;
-          gc0 = gcp[0]; gc1 = gcp[1]; gc2 = gcp[2];
-          sv = a.sem[(size_t)b * a.sem_stride + ray];
-          mv = a.mask[(size_t)b * a.mask_stride + ray];
+        // ---- E0: positional embedding (embedding.py:82-91) ------------------------------
+        const float t0x = nx * isc, t1x = ny * isc, t2x = nz * isc, zv = nzv;
+        const float gd = n_gd, gc0 = n_c0, gc1 = n_c1, gc2 = n_c2;
+        const int smv = n_sm;
+        prefetch(t + 2);
+        if (hsel == 0) {
+          sc[R_Z * 128 + p] = zv; sc[R_T0 * 128 + p] = t0x; sc[R_T1 * 128 + p] = t1x; sc[R_T2 * 128 + p] = t2x;
         }
         {
-          const float* Bd = wf + F_DIRS;
-          uint4* e1 = reinterpret_cast<uint4*>(act + FG_E1 * FGB + tg * 16);
-          uint4* e2 = reinterpret_cast<uint4*>(act + FG_E2 * FGB + tg * 16);
-          float s[6], c[6];
-          // direction 20 shares chunk 0 of emb1 with [1, x, y, z] and chunk 5 of emb2 with the const-1 column
-          sincos_ladder(fmaf(Bd[62], t2x, fmaf(Bd[61], t1x, Bd[60] * t0x)), s, c);
-          e1[0] = make_uint4(pack_h2(1.0f, t0x), pack_h2(t1x, t2x), pack_h2(s[0], s[1]), pack_h2(s[2], s[3]));
-          e2[5 * 128] = make_uint4(pack_h2(s[4], s[5]), pack_h2(1.0f, 0.f), 0u, 0u);
-          e1[11 * 128] = make_uint4(0u, 0u, 0u, 0u);
-          uint32_t hold[4];
-#pragma unroll
-          for (int i = 0; i < 10; ++i) {
-            float sa[6], ca[6], sb[6], cb[6];
-            const int d0 = 2 * i, d1 = 2 * i + 1;
-            sincos_ladder(fmaf(Bd[d0 * 3 + 2], t2x, fmaf(Bd[d0 * 3 + 1], t1x, Bd[d0 * 3] * t0x)), sa, ca);
-            sincos_ladder(fmaf(Bd[d1 * 3 + 2], t2x, fmaf(Bd[d1 * 3 + 1], t1x, Bd[d1 * 3] * t0x)), sb, cb);
-            e1[(i + 1) * 128] = make_uint4(pack_h2(sa[0], sa[1]), pack_h2(sa[2], sa[3]), pack_h2(sb[0], sb[1]), pack_h2(sb[2], sb[3]));
-            if ((i & 1) == 0) { hold[0] = pack_h2(sa[4], sa[5]); hold[1] = pack_h2(sb[4], sb[5]); }
-            else { e2[(i >> 1) * 128] = make_uint4(hold[0], hold[1], pack_h2(sa[4], sa[5]), pack_h2(sb[4], sb[5])); }
+          uint4* e1 = reinterpret_cast<uint4*>(act + FG_E1 * FGB + p * 16);
+          uint4* e2 = reinterpret_cast<uint4*>(act + FG_E2 * FGB + p * 16);
+          const int q0 = hsel ? 3 : 0, q1 = hsel ? 5 : 3;
+#pragma unroll 1
+          for (int q = q0; q < q1; ++q) {              // directions 4q .. 4q+3
+            const float* bq = Bd + q * 12;
+            float sa[6], sb[6];
+            sin_ladder(fmaf(bq[2], t2x, fmaf(bq[1], t1x, bq[0] * t0x)), sa);
+            sin_ladder(fmaf(bq[5], t2x, fmaf(bq[4], t1x, bq[3] * t0x)), sb);
+            e1[(2 * q + 1) * 128] = make_uint4(pack_h2(sa[0], sa[1]), pack_h2(sa[2], sa[3]), pack_h2(sb[0], sb[1]), pack_h2(sb[2], sb[3]));
+            const uint32_t h0 = pack_h2(sa[4], sa[5]), h1 = pack_h2(sb[4], sb[5]);
+            sin_ladder(fmaf(bq[8], t2x, fmaf(bq[7], t1x, bq[6] * t0x)), sa);
+            sin_ladder(fmaf(bq[11], t2x, fmaf(bq[10], t1x, bq[9] * t0x)), sb);
+            e1[(2 * q + 2) * 128] = make_uint4(pack_h2(sa[0], sa[1]), pack_h2(sa[2], sa[3]), pack_h2(sb[0], sb[1]), pack_h2(sb[2], sb[3]));
+            e2[q * 128] = make_uint4(h0, h1, pack_h2(sa[4], sa[5]), pack_h2(sb[4], sb[5]));
           }
-          // zero this point's dhead row (cols 4..15 stay zero; 0..3 are written by the ray thread)
-          uint4* dh = reinterpret_cast<uint4*>(act + FG_DH * FGB + tg * 16);
-          dh[0] = make_uint4(0u, 0u, 0u, 0u); dh[128] = make_uint4(0u, 0u, 0u, 0u);
+          if (hsel) {
+            // direction 20 shares chunk 0 of emb1 with [1, x, y, z] and chunk 5 of emb2 with the const-1 column
+            float s[6];
+            sin_ladder(fmaf(Bd[62], t2x, fmaf(Bd[61], t1x, Bd[60] * t0x)), s);
+            e1[0] = make_uint4(pack_h2(1.0f, t0x), pack_h2(t1x, t2x), pack_h2(s[0], s[1]), pack_h2(s[2], s[3]));
+            e2[5 * 128] = make_uint4(pack_h2(s[4], s[5]), pack_h2(1.0f, 0.f), 0u, 0u);
+            e1[11 * 128] = make_uint4(0u, 0u, 0u, 0u);
+            // zero this point's dhead row (cols 4..15 stay zero; 0..3 are written after the render)
+            uint4* dh = reinterpret_cast<uint4*>(act + FG_DH * FGB + p * 16);
+            dh[0] = make_uint4(0u, 0u, 0u, 0u); dh[128] = make_uint4(0u, 0u, 0u, 0u);
+          }
         }
-        uint32_t m1, m2, m3, m4, mc;
-
-        // hidden-layer epilogue: acc + bias -> ReLU -> fp16 row (4 x 16 B), returns the sign mask
-#define EPI_RELU(TADDR, BIAS_OFF, FG, MASK)                                                    \
-  do {                                                                                         \
-    float v[32];                                                                               \
-    ptx::tmem_ld32(TADDR, v);                                                                  \
-    ptx::tmem_ld_wait();                                                                       \
-    uint32_t mk = 0;                                                                           \
-    _Pragma("unroll") for (int j = 0; j < 32; ++j) {                                           \
-      const float x = v[j] + wf[(BIAS_OFF) + j];                                               \
-      if (x > 0.f) { mk |= 1u << j; v[j] = x; } else v[j] = 0.f;                               \
-    }                                                                                          \
-    MASK = mk;                                                                                 \
-    uint4* dst = reinterpret_cast<uint4*>(act + (FG) * FGB + tg * 16);                         \
-    _Pragma("unroll") for (int q = 0; q < 4; ++q)                                              \
-      dst[q * 128] = make_uint4(pack_h2(v[8 * q], v[8 * q + 1]), pack_h2(v[8 * q + 2], v[8 * q + 3]), \
-                                pack_h2(v[8 * q + 4], v[8 * q + 5]), pack_h2(v[8 * q + 6], v[8 * q + 7])); \
-  } while (0)
-        // dgrad epilogue: dY = relu'(h) * acc -> fp16 row written over h
-#define EPI_DGRAD(TADDR, FG, MASK)                                                             \
-  do {                                                                                         \
-    float v[32];                                                                               \
-    ptx::tmem_ld32(TADDR, v);                                                                  \
-    ptx::tmem_ld_wait();                                                                       \
-    _Pragma("unroll") for (int j = 0; j < 32; ++j) v[j] = ((MASK >> j) & 1u) ? clamp_h(v[j]) : 0.f; \
-    uint4* dst = reinterpret_cast<uint4*>(act + (FG) * FGB + tg * 16);                         \
-    _Pragma("unroll") for (int q = 0; q < 4; ++q)                                              \
-      dst[q * 128] = make_uint4(pack_h2(v[8 * q], v[8 * q + 1]), pack_h2(v[8 * q + 2], v[8 * q + 3]), \
-                                pack_h2(v[8 * q + 4], v[8 * q + 5]), pack_h2(v[8 * q + 6], v[8 * q + 7])); \
-  } while (0)
-
         STAGE_SYNC();                               // st0: in_layer
-        EPI_RELU(tA, F_BIN, FG_FC1, m1);
+        EPI_RELU(tA, F_BIN, FG_FC1);
         STAGE_SYNC();                               // st1: mid1
-        EPI_RELU(tB, F_BM1, FG_FC2, m2);
+        EPI_RELU(tB, F_BM1, FG_FC2);
         STAGE_SYNC();                               // st2: cat_layer
-        EPI_RELU(tA, F_BCAT, FG_FC3, m3);
+        EPI_RELU(tA, F_BCAT, FG_FC3);
         STAGE_SYNC();                               // st3: mid2
-        EPI_RELU(tB, F_BM2, FG_FC4, m4);
+        EPI_RELU(tB, F_BM2, FG_FC4);
         STAGE_SYNC();                               // st4: color_linear + out_alpha
-        EPI_RELU(tA, F_BCL, FG_HC, mc);
+        EPI_RELU(tA, F_BCL, FG_HC);
         STAGE_SYNC();                               // st5: out_color
-        {
-          float v[16];
-          ptx::tmem_ld16(tB, v);
+        // ---- heads: alpha*10 -> sigmoid occupancy, colour sigmoid (model.py:77,83; render_rays.py:6)
+        float occ = 0.f, c0 = 0.f, c1 = 0.f, c2 = 0.f;
+        if (hsel == 0) {
+          float v[8];
+          tmem_ld8(tB, v);
           ptx::tmem_ld_wait();
-          sc[0 * 128 + tg] = (v[0] + wf[F_BA]) * 10.0f;                      // model.py:77
-          sc[1 * 128 + tg] = vmb_sigmoid(v[1] + wf[F_BOC + 0]);              // model.py:83
-          sc[2 * 128 + tg] = vmb_sigmoid(v[2] + wf[F_BOC + 1]);
-          sc[3 * 128 + tg] = vmb_sigmoid(v[3] + wf[F_BOC + 2]);
+          occ = vmb_sigmoid((v[0] + wf[F_BA]) * 10.0f);
+          c0 = vmb_sigmoid(v[1] + wf[F_BOC + 0]); c1 = vmb_sigmoid(v[2] + wf[F_BOC + 1]); c2 = vmb_sigmoid(v[3] + wf[F_BOC + 2]);
+          sc[R_OCC * 128 + p] = occ; sc[R_F * 128 + p] = 1.f - occ + 1e-10f;
+          sc[R_C0 * 128 + p] = c0; sc[R_C1 * 128 + p] = c1; sc[R_C2 * 128 + p] = c2;
         }
         group_bar(g);
-        // ---- volume render + loss + d(loss)/d(raw alpha, raw colour) on the ray threads --
-        if (is_ray) {
-          const int ray = r0 + tg, pb = tg * S;
-          float occ_[UMMA_MAX_S], T_[UMMA_MAX_S];
-          float Tr = 1.f, D = 0.f, O = 0.f, C0 = 0.f, C1 = 0.f, C2 = 0.f;
-          for (int s = 0; s < S; ++s) {
-            const int q = pb + s;
-            const float occ = vmb_sigmoid(sc[q]);
-            const float w = occ * Tr;
-            occ_[s] = occ; T_[s] = Tr;
-            D = fmaf(w, sc[4 * 128 + q], D); O += w;
-            C0 = fmaf(w, sc[1 * 128 + q], C0); C1 = fmaf(w, sc[2 * 128 + q], C1); C2 = fmaf(w, sc[3 * 128 + q], C2);
-            Tr *= (1.f - occ + 1e-10f);
-          }
-          float V = 0.f;
-          for (int s = 0; s < S; ++s) { const float dz = sc[4 * 128 + pb + s] - D; V = fmaf(occ_[s] * T_[s], dz * dz, V); }
-          if (a.r_depth) a.r_depth[(size_t)b * R + ray] = D;
-          if (a.r_var) a.r_var[(size_t)b * R + ray] = V;
-          if (a.r_opacity) a.r_opacity[(size_t)b * R + ray] = O;
-          if (a.r_colour) { float* rc = a.r_colour + ((size_t)b * R + ray) * 3; rc[0] = C0; rc[1] = C1; rc[2] = C2; }
-          const float m_o = (sv != 0) ? 1.f : 0.f, m_s = (sv != 2) ? 1.f : 0.f, m_d = (mv != 0) ? m_o : 0.f;
-          const float info = 1.f / (sqrtf(V) + 1e-4f);
-          const float e_d = D - gd, e_o = O - m_o, e_c0 = C0 - gc0, e_c1 = C1 - gc1, e_c2 = C2 - gc2;
-          ls_d += on_d * fabsf(e_d) * m_d * info * inv_nd;
-          ls_c += on_c * (fabsf(e_c0) + fabsf(e_c1) + fabsf(e_c2)) * m_o * inv_no;
-          ls_o += on_o * fabsf(e_o) * m_s * inv_ns;
-          if (a.backward) {
-            const float gD = LS * on_d * vmb_sign(e_d) * m_d * info * inv_nd;
-            const float kc = LS * on_c * a.cs * m_o * inv_no;
-            const float gC0 = kc * vmb_sign(e_c0), gC1 = kc * vmb_sign(e_c1), gC2 = kc * vmb_sign(e_c2);
-            const float gO = LS * on_o * a.os * vmb_sign(e_o) * m_s * inv_ns;
-            float suffix = 0.f;
-            for (int s = S - 1; s >= 0; --s) {
+        // ---- per-ray: termination weights, rendered depth/colour/opacity, losses, ray gradients
+        if (hsel == 1 && p < nr) {
+          float gD = 0.f, gC0 = 0.f, gC1 = 0.f, gC2 = 0.f, gO = 0.f;
+          if (smv & 0x10000) {
+            const int ray = r0 + p, pb = p * S;
+            float Tr = 1.f, D = 0.f, O = 0.f, C0 = 0.f, C1 = 0.f, C2 = 0.f;
+            for (int s = 0; s < S; ++s) {
               const int q = pb + s;
-              const float occ = occ_[s], Ts = T_[s], w = occ * Ts;
-              const float c0 = sc[1 * 128 + q], c1 = sc[2 * 128 + q], c2 = sc[3 * 128 + q];
-              const float Gs = fmaf(gD, sc[4 * 128 + q], fmaf(gC0, c0, fmaf(gC1, c1, fmaf(gC2, c2, gO))));
-              const float docc = Gs * Ts - suffix / (1.f - occ + 1e-10f);
-              const float da = clamp_h(10.0f * docc * occ * (1.f - occ));
-              const float d0 = clamp_h(gC0 * w * c0 * (1.f - c0)), d1 = clamp_h(gC1 * w * c1 * (1.f - c1));
-              const float d2 = clamp_h(gC2 * w * c2 * (1.f - c2));
-              *reinterpret_cast<uint2*>(act + FG_DH * FGB + q * 16) = make_uint2(pack_h2(da, d0), pack_h2(d1, d2));
-              suffix = fmaf(Gs, w, suffix);
+              const float w = sc[R_OCC * 128 + q] * Tr;                 // render_rays.py:34
+              sc[R_W * 128 + q] = w; sc[R_T * 128 + q] = Tr;
+              D = fmaf(w, sc[R_Z * 128 + q], D); O += w;
+              C0 = fmaf(w, sc[R_C0 * 128 + q], C0); C1 = fmaf(w, sc[R_C1 * 128 + q], C1); C2 = fmaf(w, sc[R_C2 * 128 + q], C2);
+              Tr *= sc[R_F * 128 + q];                                  // render_rays.py:29
+            }
+            float V = 0.f;
+            for (int s = 0; s < S; ++s) { const float dz = sc[R_Z * 128 + pb + s] - D; V = fmaf(sc[R_W * 128 + pb + s], dz * dz, V); }
+            if (a.r_depth) a.r_depth[(size_t)b * R + ray] = D;
+            if (a.r_var) a.r_var[(size_t)b * R + ray] = V;
+            if (a.r_opacity) a.r_opacity[(size_t)b * R + ray] = O;
+            if (a.r_colour) { float* rc = a.r_colour + ((size_t)b * R + ray) * 3; rc[0] = C0; rc[1] = C1; rc[2] = C2; }
+            const int sv = smv & 0xff, mv = (smv >> 8) & 0xff;
+            const float m_o = (sv != 0) ? 1.f : 0.f, m_s = (sv != 2) ? 1.f : 0.f, m_d = (mv != 0) ? m_o : 0.f;
+            const float info = 1.f / (sqrtf(V) + 1e-4f);                // render_rays.py:74-79
+            const float e_d = D - gd, e_o = O - m_o, e_c0 = C0 - gc0, e_c1 = C1 - gc1, e_c2 = C2 - gc2;
+            ls_d += on_d * fabsf(e_d) * m_d * info * inv_nd;
+            ls_c += on_c * (fabsf(e_c0) + fabsf(e_c1) + fabsf(e_c2)) * m_o * inv_no;
+            ls_o += on_o * fabsf(e_o) * m_s * inv_ns;
+            gD = LS * on_d * vmb_sign(e_d) * m_d * info * inv_nd;
+            const float kc = LS * on_c * a.cs * m_o * inv_no;
+            gC0 = kc * vmb_sign(e_c0); gC1 = kc * vmb_sign(e_c1); gC2 = kc * vmb_sign(e_c2);
+            gO = LS * on_o * a.os * vmb_sign(e_o) * m_s * inv_ns;
+          }
+          rb[p] = gD; rb[128 + p] = gC0; rb[256 + p] = gC1; rb[384 + p] = gC2; rb[512 + p] = gO;
+        }
+        group_bar(g);
+        if (!a.backward) continue;
+        // ---- per-point: d(loss)/d(raw alpha, raw colour) through the termination product ---
+        float Gs = 0.f, gC0 = 0.f, gC1 = 0.f, gC2 = 0.f, wq = 0.f;
+        const bool pv = (hsel == 0) && (p < np) && (r0 + rl < R);
+        if (pv) {
+          gC0 = rb[128 + rl]; gC1 = rb[256 + rl]; gC2 = rb[384 + rl];
+          Gs = fmaf(rb[rl], zv, fmaf(gC0, c0, fmaf(gC1, c1, fmaf(gC2, c2, rb[512 + rl]))));
+          wq = sc[R_W * 128 + p];
+          sc[R_GW * 128 + p] = Gs * wq;
+        }
+        group_bar(g);
+        if (pv) {
+          float suffix = 0.f;                                            // sum_{k>s} G_k w_k
+          for (int k = sidx + 1; k < S; ++k) suffix += sc[R_GW * 128 + p - sidx + k];
+          const float docc = Gs * sc[R_T * 128 + p] - suffix / (1.f - occ + 1e-10f);
+          const float da = 10.0f * docc * occ * (1.f - occ);             // model.py:77
+          *reinterpret_cast<uint2*>(act + FG_DH * FGB + p * 16) =
+              make_uint2(pack_h2(da, gC0 * wq * c0 * (1.f - c0)), pack_h2(gC1 * wq * c1 * (1.f - c1), gC2 * wq * c2 * (1.f - c2)));
+        }
+        STAGE_SYNC();                               // st6: d_hc (+ wgrad heads)
+        EPI_DGRAD(tA, FG_HC);
+        STAGE_SYNC();                               // st7: d_fc4 (+ wgrad color_linear)
+        EPI_DGRAD(tB, FG_FC4);
+        STAGE_SYNC();                               // st8: d_fc3 (+ wgrad mid2)
+        EPI_DGRAD(tA, FG_FC3);
+        STAGE_SYNC();                               // st9: d_fc2, d_emb1 part 1 (+ wgrad cat_layer)
+        EPI_DGRAD(tB, FG_FC2);
+        STAGE_SYNC();                               // st10: d_fc1 (+ wgrad mid1)
+        EPI_DGRAD(tA, FG_FC1);
+        STAGE_SYNC();                               // st11: d_emb1 part 2 -> E, d_emb2 -> A[0..48) (+ wgrad in_layer)
+        // ---- PE backward: dproj_d = pi * sum_k 2^k g_{k,d} cos(pi 2^k proj_d) ------------
+        {
+          const int q0 = hsel ? 3 : 0, q1 = hsel ? 5 : 3;
+#pragma unroll 1
+          for (int q = q0; q < q1; ++q) {
+            float g1a[8], g1b[8], g2[8];
+            tmem_ld8(tE + 16 * q + 8, g1a);           // emb1 cols of directions 4q, 4q+1 (k = 0..3)
+            tmem_ld8(tE + 16 * q + 16, g1b);          //                          4q+2, 4q+3
+            tmem_ld8(tA + 8 * q, g2);                 // emb2 cols (k = 4, 5)
+            ptx::tmem_ld_wait();
+            const float* bq = Bd + q * 12;
+#pragma unroll
+            for (int dd = 0; dd < 4; ++dd) {
+              float c[6];
+              cos_ladder(fmaf(bq[dd * 3 + 2], t2x, fmaf(bq[dd * 3 + 1], t1x, bq[dd * 3] * t0x)), c);
+              const float* g1 = (dd < 2) ? (g1a + dd * 4) : (g1b + (dd - 2) * 4);
+              float dp = g1[0] * c[0];
+              dp = fmaf(2.f * g1[1], c[1], dp);
+              dp = fmaf(4.f * g1[2], c[2], dp);
+              dp = fmaf(8.f * g1[3], c[3], dp);
+              dp = fmaf(16.f * g2[dd * 2], c[4], dp);
+              dp = fmaf(32.f * g2[dd * 2 + 1], c[5], dp);
+              dpr[(4 * q + dd) * 128 + p] = dp * VMB_PI_F;
             }
           }
-        }
-        if (!a.backward) { group_bar(g); continue; }
-
-        STAGE_SYNC();                               // st6: d_hc (+ wgrad heads)
-        EPI_DGRAD(tA, FG_HC, mc);
-        STAGE_SYNC();                               // st7: d_fc4, d_emb2 (+ wgrad color_linear)
-        EPI_DGRAD(tB, FG_FC4, m4);
-        uint32_t ge2[21];                           // (g_k4, g_k5) per direction, packed fp16
-        {
-          float v[32];
-          ptx::tmem_ld32(tE, v);
-          ptx::tmem_ld_wait();
-#pragma unroll
-          for (int d = 0; d < 16; ++d) ge2[d] = pack_h2(clamp_h(v[2 * d]), clamp_h(v[2 * d + 1]));
-          float u[16];
-          ptx::tmem_ld16(tE + 32, u);
-          ptx::tmem_ld_wait();
-#pragma unroll
-          for (int d = 16; d < 21; ++d) ge2[d] = pack_h2(clamp_h(u[2 * (d - 16)]), clamp_h(u[2 * (d - 16) + 1]));
-        }
-        STAGE_SYNC();                               // st8: d_fc3 (+ wgrad mid2)
-        EPI_DGRAD(tA, FG_FC3, m3);
-        STAGE_SYNC();                               // st9: d_fc2, d_emb1 part 1 (+ wgrad cat_layer)
-        EPI_DGRAD(tB, FG_FC2, m2);
-        STAGE_SYNC();                               // st10: d_fc1 (+ wgrad mid1)
-        EPI_DGRAD(tA, FG_FC1, m1);
-        STAGE_SYNC();                               // st11: d_emb1 part 2 (+ wgrad in_layer)
-        // ---- PE backward: dproj_d = pi * sum_k 2^k g_{k,d} cos(pi 2^k proj_d); dB += dproj^T t
-        {
-          const float* Bd = wf + F_DIRS;
-          float v[32];
-#pragma unroll
-          for (int blk = 0; blk < 3; ++blk) {
-            ptx::tmem_ld32(tE + blk * 32, v);
+          if (hsel) {                                 // direction 20: emb1 cols 4..7, emb2 cols 40, 41
+            float g1[8], g2[8], c[6];
+            tmem_ld8(tE, g1);
+            tmem_ld8(tA + 40, g2);
             ptx::tmem_ld_wait();
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              // 4 columns per direction; block 0 starts with [1, x, y, z] then direction 20
-              int d;
-              if (blk == 0 && e == 0) continue;
-              if (blk == 0 && e == 1) d = 20; else d = 2 * (blk * 4 + (e >> 1) - 1) + (e & 1);
-              if (d > 19 && !(blk == 0 && e == 1)) continue;
-              float s[6], c[6];
-              sincos_ladder(fmaf(Bd[d * 3 + 2], t2x, fmaf(Bd[d * 3 + 1], t1x, Bd[d * 3] * t0x)), s, c);
-              const __half2 h45 = *reinterpret_cast<const __half2*>(&ge2[d]);
-              float dp = v[e * 4] * c[0];
-              dp = fmaf(2.f * v[e * 4 + 1], c[1], dp);
-              dp = fmaf(4.f * v[e * 4 + 2], c[2], dp);
-              dp = fmaf(8.f * v[e * 4 + 3], c[3], dp);
-              dp = fmaf(16.f * __low2float(h45), c[4], dp);
-              dp = fmaf(32.f * __high2float(h45), c[5], dp);
-              dp *= VMB_PI_F;
-              dBacc[d * 3 + 0] = fmaf(dp, t0x, dBacc[d * 3 + 0]);
-              dBacc[d * 3 + 1] = fmaf(dp, t1x, dBacc[d * 3 + 1]);
-              dBacc[d * 3 + 2] = fmaf(dp, t2x, dBacc[d * 3 + 2]);
-            }
+            cos_ladder(fmaf(Bd[62], t2x, fmaf(Bd[61], t1x, Bd[60] * t0x)), c);
+            float dp = g1[4] * c[0];
+            dp = fmaf(2.f * g1[5], c[1], dp); dp = fmaf(4.f * g1[6], c[2], dp); dp = fmaf(8.f * g1[7], c[3], dp);
+            dp = fmaf(16.f * g2[0], c[4], dp); dp = fmaf(32.f * g2[1], c[5], dp);
+            dpr[20 * 128 + p] = dp * VMB_PI_F;
           }
         }
         ptx::tc_fence_before();
-        group_bar(g);                               // everyone is done with sc / TMEM before the next tile
+        group_bar(g);
         ptx::tc_fence_after();
+        {   // dB[d][i] += sum_p dproj[d][p] * t_i[p]  (embedding.py:84): 63 outputs x 4 point quarters
+          const int o = tg & 63, quarter = tg >> 6;
+          if (o < 63) {
+            const int d = o / 3, i = o - d * 3;
+            const float* dp = dpr + d * 128 + quarter * 32;
+            const float* tp = sc + (R_T0 + i) * 128 + quarter * 32;
+            float acc = 0.f;
+#pragma unroll 8
+            for (int k = 0; k < 32; ++k) acc = fmaf(dp[k], tp[k], acc);
+            atomicAdd(&dbs[o], acc);
+          }
+        }
+        group_bar(g);                               // scratch is free for the next tile
       }
 #undef STAGE_SYNC
 #undef EPI_RELU
 #undef EPI_DGRAD
-      // ---- per-(CTA, object) flush of the register-resident partial sums ----------------
+      // ---- per-(CTA, object) flush of the partial sums ---------------------------------------
       ls_d = warp_sum(ls_d); ls_c = warp_sum(ls_c); ls_o = warp_sum(ls_o);
-      if ((tid & 31) == 0 && a.loss_terms) {
+      if ((tid & 31) == 0 && a.loss_terms && hsel == 1) {
         atomicAdd(a.loss_terms + b * 4 + 0, ls_d); atomicAdd(a.loss_terms + b * 4 + 1, ls_c);
         atomicAdd(a.loss_terms + b * 4 + 2, ls_o);
         atomicAdd(a.loss_terms + b * 4 + 3, ls_d + a.cs * ls_c + a.os * ls_o);
       }
-      if (a.backward) {
-        float* G = a.grads + (size_t)b * L.stride + L.o_B;
-#pragma unroll
-        for (int i = 0; i < 63; ++i) {
-          const float s = warp_sum(dBacc[i]);
-          if ((tid & 31) == 0) atomicAdd(G + i, s * INV_LS);
-        }
-      }
+      if (a.backward && tg < 63) atomicAdd(a.grads + (size_t)b * L.stride + L.o_B + tg, dbs[tg] * INV_LS);
     }
 
     // ---- segment end: all MMAs have completed (each group waited on its last commit) -----
@@ -622,7 +676,7 @@ k_step_umma(StepParams a, VmbLayout L, const unsigned char* __restrict__ image, 
     ptx::tc_fence_after();
   }
 
-  if (warp == 8) ptx::tmem_dealloc(tm, 512);
+  if (warp == 16) ptx::tmem_dealloc(tm, 512);
 }
 
 // ---------------------------------------------------------------------------------------

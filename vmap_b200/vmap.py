@@ -1,0 +1,216 @@
+"""sceneObject / cameraInfo / performance_measure with the reference's call surface
+(vmap.py:17-29, 90-491, 494-524).  The keyframe buffers are the reference's tensors
+(same shapes / dtypes, images stored [W, H]); the arithmetic of
+``get_training_samples`` (vmap.py:319-459) runs in the batched CUDA sampler (K3):
+``sample_all`` draws for every object of the frame in ONE launch (replacing the Python
+loop of train.py:208-218 and the stack + /255 of train.py:255-260), and the per-object
+method is the same kernel with one object.
+"""
+from __future__ import annotations
+
+import copy
+import os
+import random
+from time import perf_counter_ns
+from typing import Dict, List, Optional
+
+import torch
+
+from . import trainer as trainer_mod
+from .sampler import BatchedSampler, KeyframeSet
+
+
+class performance_measure:
+    """Wall-clock context manager that prints ms (vmap.py:17-29); kept as the reference's
+    only timing hook.  Pass ``sync=True`` to bracket with cuda synchronize."""
+
+    def __init__(self, name, sync: bool = False) -> None:
+        self.name, self.sync = name, sync
+
+    def __enter__(self):
+        if self.sync and torch.cuda.is_available():
+            torch.cuda.synchronize()
+        self.start_time = perf_counter_ns()
+
+    def __exit__(self, type, value, tb):
+        if self.sync and torch.cuda.is_available():
+            torch.cuda.synchronize()
+        self.end_time = perf_counter_ns()
+        self.exec_time = self.end_time - self.start_time
+        print(f"{self.name} excution time: {(self.exec_time)/1000000:.2f} ms")
+
+
+class cameraInfo:
+    """Ray-direction cache [W,H,3] = ((u-cx)/fx, (v-cy)/fy, 1) (vmap.py:494-524)."""
+
+    def __init__(self, cfg) -> None:
+        self.device = cfg.data_device
+        self.width, self.height = cfg.W, cfg.H
+        self.fx, self.fy, self.cx, self.cy = cfg.fx, cfg.fy, cfg.cx, cfg.cy
+        self.rays_dir_cache = self.get_rays_dirs()
+
+    def get_rays_dirs(self, depth_type="z"):
+        if depth_type != "z":
+            raise Exception("Get camera rays directions with euclidean depth not yet implemented")
+        u = (torch.arange(self.width, device=self.device) - self.cx) / self.fx
+        v = (torch.arange(self.height, device=self.device) - self.cy) / self.fy
+        dirs = torch.ones((self.width, self.height, 3), device=self.device)
+        dirs[:, :, 0] = u[:, None]
+        dirs[:, :, 1] = v
+        return dirs
+
+
+_SAMPLERS: Dict[tuple, BatchedSampler] = {}
+_CALLS = [0]
+
+
+def _sampler_for(obj) -> BatchedSampler:
+    key = (str(obj.data_device), obj.n_bins_cam2surface, obj.n_bins, obj.surface_eps, obj.stop_eps, obj.min_bound)
+    if key not in _SAMPLERS:
+        _SAMPLERS[key] = BatchedSampler(obj.data_device, obj.n_bins_cam2surface, obj.n_bins, obj.surface_eps,
+                                        obj.stop_eps, obj.min_bound)
+    return _SAMPLERS[key]
+
+
+def sample_all(objects: List["sceneObject"], n_frames: int, n_samples: int, cached_rays_dir: torch.Tensor,
+               seed: Optional[int] = None) -> Dict[str, torch.Tensor]:
+    """One launch for every object: stacked {pcs [B,N,S,3], z [B,N,S], gt_depth [B,N],
+    gt_colour [B,N,3] (already /255), sem [B,N] u8, mask_depth [B,N] bool}, N = n_frames*n_samples.
+    All objects must share the sampling configuration (objects vs. the background model differ)."""
+    smp = _sampler_for(objects[0])
+    _CALLS[0] += 1
+    if seed is None:
+        seed = torch.initial_seed() & 0x7FFFFFFFFFFFFFFF
+    return smp.sample([o.keyframe_set() for o in objects], n_frames, n_samples, cached_rays_dir,
+                      seed=seed, offset=_CALLS[0])
+
+
+class sceneObject:
+    """Per-object keyframe buffers + sampler entry point (vmap.py:90-491)."""
+
+    def __init__(self, cfg, obj_id, rgb: torch.Tensor, depth: torch.Tensor, mask: torch.Tensor,
+                 bbox_2d: torch.Tensor, t_wc: torch.Tensor, live_frame_id) -> None:
+        self.do_bg = cfg.do_bg
+        self.obj_id = obj_id
+        self.data_device = cfg.data_device
+        self.training_device = cfg.training_device
+        assert rgb.shape[:2] == depth.shape and rgb.shape[:2] == mask.shape
+        assert bbox_2d.shape == (4,) and t_wc.shape == (4, 4)
+        bg = self.do_bg and self.obj_id == 0                     # vmap.py:109-118
+        self.obj_scale = cfg.bg_scale if bg else cfg.obj_scale
+        self.hidden_feature_size = cfg.hidden_feature_size_bg if bg else cfg.hidden_feature_size
+        self.n_bins_cam2surface = cfg.n_bins_cam2surface_bg if bg else cfg.n_bins_cam2surface
+        self.keyframe_step = cfg.keyframe_step_bg if bg else cfg.keyframe_step
+        self.frames_width, self.frames_height = rgb.shape[0], rgb.shape[1]
+        self.min_bound, self.max_bound = cfg.min_depth, cfg.max_depth
+        self.n_bins, self.n_unidir_funcs = cfg.n_bins, cfg.n_unidir_funcs
+        self.surface_eps, self.stop_eps = cfg.surface_eps, cfg.stop_eps
+        self.n_keyframes = 1
+        self.kf_pointer = None
+        self.keyframe_buffer_size = cfg.keyframe_buffer_size
+        self.kf_id_dict = {live_frame_id: 0}                     # frame id -> buffer slot
+        self.kf_buffer_full = False
+        self.frame_cnt = 0
+        self.lastest_kf_queue = []
+        KF, W, H, dev = self.keyframe_buffer_size, self.frames_width, self.frames_height, self.data_device
+        self.bbox = torch.empty(KF, 4, device=dev)               # [u low, u high, v low, v high]
+        self.rgb_idx, self.state_idx = slice(0, 3), slice(3, 4)
+        self.rgbs_batch = torch.empty(KF, W, H, 4, dtype=torch.uint8, device=dev)
+        self.other_obj, self.this_obj, self.unknown_obj = 0, 1, 2
+        self.depth_batch = torch.empty(KF, W, H, dtype=torch.float32, device=dev)
+        self.t_wc_batch = torch.empty(KF, 4, 4, dtype=torch.float32, device=dev)
+        self._store(0, rgb, depth, mask, bbox_2d, t_wc)
+        tcfg = copy.deepcopy(cfg)
+        tcfg.obj_id, tcfg.hidden_feature_size, tcfg.obj_scale = self.obj_id, self.hidden_feature_size, self.obj_scale
+        self.trainer = trainer_mod.Trainer(tcfg)
+        self.bbox3d = None
+        self.pc = []
+        self.obj_center = torch.tensor(0.0)
+
+    def _store(self, slot, rgb, depth, mask, bbox_2d, t_wc):
+        self.rgbs_batch[slot, :, :, self.rgb_idx] = rgb
+        self.rgbs_batch[slot, :, :, self.state_idx] = mask[..., None]
+        self.depth_batch[slot] = depth
+        self.t_wc_batch[slot] = t_wc
+        self.bbox[slot] = bbox_2d
+
+    def _slot_to_frame(self, slot, frame_id):
+        for k in [k for k, v in self.kf_id_dict.items() if v == slot]:
+            del self.kf_id_dict[k]
+        self.kf_id_dict[frame_id] = slot
+
+    def append_keyframe(self, rgb, depth, mask, bbox_2d, t_wc, frame_id=1):
+        """vmap.py:208-263: a new keyframe every ``keyframe_step`` frames, otherwise the newest
+        slot is overwritten; once the buffer is full a random old keyframe is recycled."""
+        assert rgb.shape[:2] == depth.shape and rgb.shape[:2] == mask.shape
+        assert bbox_2d.shape == (4,) and t_wc.shape == (4, 4)
+        assert self.n_keyframes <= self.keyframe_buffer_size - 1
+        assert rgb.dtype == torch.uint8 and mask.dtype == torch.uint8 and depth.dtype == torch.float32
+        is_kf = (self.frame_cnt % self.keyframe_step == 0) or self.n_keyframes == 1
+        if self.n_keyframes == self.keyframe_buffer_size - 1:
+            self.kf_buffer_full = True
+            if self.kf_pointer is None:
+                self.kf_pointer = self.n_keyframes
+            self._store(self.kf_pointer, rgb, depth, mask, bbox_2d, t_wc)
+            self._slot_to_frame(self.kf_pointer, frame_id)
+            if is_kf:
+                self.lastest_kf_queue.append(self.kf_pointer)
+                _, self.kf_pointer = self.prune_keyframe()
+                print("pruned kf id ", self.kf_pointer)
+        elif not is_kf:
+            self._store(self.n_keyframes - 1, rgb, depth, mask, bbox_2d, t_wc)
+            self._slot_to_frame(self.n_keyframes - 1, frame_id)
+        else:
+            self.kf_id_dict[frame_id] = self.n_keyframes
+            self._store(self.n_keyframes, rgb, depth, mask, bbox_2d, t_wc)
+            self.lastest_kf_queue.append(self.n_keyframes)
+            self.n_keyframes += 1
+        self.frame_cnt += 1
+        if len(self.lastest_kf_queue) > 2:
+            self.lastest_kf_queue = self.lastest_kf_queue[-2:]
+
+    def prune_keyframe(self):
+        return random.choice(list(self.kf_id_dict.items())[:-2])    # never the latest two (vmap.py:265-268)
+
+    def keyframe_set(self) -> KeyframeSet:
+        latest = self.lastest_kf_queue[-2:] if len(self.lastest_kf_queue) >= 2 else [0, 0]
+        return KeyframeSet(self.rgbs_batch, self.depth_batch, self.t_wc_batch, self.bbox, self.n_keyframes, latest)
+
+    def get_training_samples(self, n_frames, n_samples, cached_rays_dir):
+        """The reference's 6-tuple (vmap.py:459): rgb [F,P,3] u8, depth [F,P], valid_depth_mask
+        [F*P] bool, obj_labels [F*P] u8, pcs [F,P,S,3], z [F,P,S]."""
+        smp = _sampler_for(self)
+        _CALLS[0] += 1
+        o = smp.sample([self.keyframe_set()], n_frames, n_samples, cached_rays_dir,
+                       seed=torch.initial_seed() & 0x7FFFFFFFFFFFFFFF, offset=_CALLS[0], want_u8=True)
+        S = o["z"].shape[-1]
+        return (o["gt_rgb_u8"][0].view(n_frames, n_samples, 3), o["gt_depth"][0].view(n_frames, n_samples),
+                o["mask_depth"][0], o["sem"][0], o["pcs"][0].view(n_frames, n_samples, S, 3),
+                o["z"][0].view(n_frames, n_samples, S))
+
+    def get_bound(self, intrinsic_open3d):
+        raise NotImplementedError("3-D bounds use open3d/trimesh on the CPU (vmap.py:270-315): out of the hot path")
+
+    def save_checkpoints(self, path, epoch):
+        """Same file layout and keys as vmap.py:461-476."""
+        f = os.path.join(path, "obj_" + str(self.obj_id) + "_frame_" + str(epoch) + ".pth")
+        torch.save({"epoch": epoch,
+                    "FC_state_dict": {k: v.detach().clone() for k, v in self.trainer.fc_occ_map.state_dict().items()},
+                    "PE_state_dict": {k: v.detach().clone() for k, v in self.trainer.pe.state_dict().items()},
+                    "obj_id": self.obj_id, "bbox": self.bbox3d, "obj_scale": self.trainer.obj_scale}, f)
+
+    def load_checkpoints(self, ckpt_file):
+        """vmap.py:478-491; parameters bound to a packed ensemble are written in place."""
+        if not os.path.exists(ckpt_file):
+            print("ckpt not exist ", ckpt_file)
+            return
+        ck = torch.load(ckpt_file, weights_only=False)
+        with torch.no_grad():
+            for k, p in self.trainer.fc_occ_map.named_parameters():
+                p.copy_(ck["FC_state_dict"][k].to(p.device))
+            self.trainer.pe.B_layer.weight.copy_(ck["PE_state_dict"]["B_layer.weight"].to(self.trainer.pe.B_layer.weight.device))
+        self.obj_id, self.bbox3d = ck["obj_id"], ck["bbox"]
+        self.trainer.obj_scale = ck["obj_scale"]
+        b = getattr(self.trainer.fc_occ_map, "_vmb_binding", None)
+        if b is not None and b[0]() is not None:
+            b[0]().refresh_image()
