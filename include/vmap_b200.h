@@ -133,6 +133,9 @@ typedef struct vmb_adam_args {
   int*   status;            /* optional device int[4], bits OR-ed in                      */
   float lr, beta1, beta2, eps, weight_decay;
   int   zero_grads;
+  int*  step_counter;       /* optional DEVICE int: when set, t = *step_counter + 1 is used instead of
+                               `step` and the counter is incremented by the kernel, so that a captured
+                               CUDA graph of the step can be replayed                              */
 } vmb_adam_args;
 
 int vmb_adam(vmb_handle* h, const vmb_adam_args* a, void* stream);

@@ -20,12 +20,27 @@ struct AdamParams {
   float bc2_sqrt;             // sqrt(1 - b2^t)
   float eps;
   int zero_grads;
+  // optional device-resident step counter (CUDA-graph replay): t = *step_counter + 1 is read by
+  // every block on entry; the last block to finish publishes it and resets the ticket.
+  int* step_counter; unsigned int* ticket;
+  double lr, b1, b2d;
 };
 
 __global__ void __launch_bounds__(256) k_adamw(AdamParams a) {
   __shared__ int s_skip;
-  if (threadIdx.x == 0) s_skip = 0;
+  __shared__ float s_step_size, s_bc2_sqrt;
+  if (threadIdx.x == 0) {
+    s_skip = 0;
+    if (a.step_counter) {
+      const double t = (double)(*a.step_counter + 1);
+      s_step_size = (float)(a.lr / (1.0 - pow(a.b1, t)));
+      s_bc2_sqrt = (float)sqrt(1.0 - pow(a.b2d, t));
+    } else {
+      s_step_size = a.step_size; s_bc2_sqrt = a.bc2_sqrt;
+    }
+  }
   __syncthreads();
+  const float step_size = s_step_size, bc2_sqrt = s_bc2_sqrt;
   if (a.loss_terms) {       // render_rays.py:88-90: the reference aborts before the update
     int bad = 0;
     for (int i = threadIdx.x; i < a.B * 4; i += blockDim.x) {
@@ -41,7 +56,7 @@ __global__ void __launch_bounds__(256) k_adamw(AdamParams a) {
     }
   }
   const long long i4 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
-  if (i4 >= a.n) return;
+  if (i4 < a.n) {
   float4 p = *reinterpret_cast<float4*>(a.p + i4);
   float4 g = *reinterpret_cast<float4*>(a.g + i4);
   float4 m = *reinterpret_cast<float4*>(a.m + i4);
@@ -52,8 +67,8 @@ __global__ void __launch_bounds__(256) k_adamw(AdamParams a) {
     float pj = pp[j] * a.lr_wd;                                  // p.mul_(1 - lr*wd)
     const float mj = mm[j] + (gg[j] - mm[j]) * a.one_m_b1;       // exp_avg.lerp_(g, 1-b1)
     const float vj = vv[j] * a.b2 + (a.one_m_b2 * gg[j]) * gg[j];// exp_avg_sq.mul_(b2).addcmul_(g,g,1-b2)
-    const float denom = sqrtf(vj) / a.bc2_sqrt + a.eps;
-    pj = pj - a.step_size * (mj / denom);                        // p.addcdiv_(m, denom, -step_size)
+    const float denom = sqrtf(vj) / bc2_sqrt + a.eps;
+    pj = pj - step_size * (mj / denom);                        // p.addcdiv_(m, denom, -step_size)
     pp[j] = pj; mm[j] = mj; vv[j] = vj;
   }
   *reinterpret_cast<float4*>(a.p + i4) = p;
@@ -71,6 +86,14 @@ __global__ void __launch_bounds__(256) k_adamw(AdamParams a) {
         if (t >= 0) img[t] = __float2half_rn(pp[j]);
         else if (t <= -2) reinterpret_cast<float*>(img)[-(t + 2)] = pp[j];
       }
+    }
+  }
+  }
+  if (a.step_counter) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      if (atomicAdd(a.ticket, 1u) == gridDim.x - 1) { *a.step_counter += 1; *a.ticket = 0u; }
     }
   }
 }

@@ -18,6 +18,7 @@ struct vmb_handle {
   VmbLayout L;
   int* d_counts;          // [max_obj][4]
   int* d_img_index;       // [P] param index -> half index inside the fp16 image (or -1)
+  unsigned int* d_ticket; // last-block ticket of the fused AdamW (device step counter mode)
   int img_halves;
   bool umma_ok;
   std::string err;
@@ -105,8 +106,10 @@ int vmb_create(vmb_handle** out, int device, int max_obj, int hidden, int n_freq
   vmb_handle* h = new vmb_handle();
   h->device = device; h->max_obj = max_obj; h->H = hidden; h->nfreq = n_freq;
   h->L = vmb_make_layout(hidden, n_freq);
-  h->d_counts = nullptr; h->d_img_index = nullptr; h->img_halves = 0; h->umma_ok = false;
+  h->d_counts = nullptr; h->d_img_index = nullptr; h->d_ticket = nullptr; h->img_halves = 0; h->umma_ok = false;
   cudaError_t e = cudaMalloc(&h->d_counts, sizeof(int) * 4 * max_obj);
+  if (e == cudaSuccess) e = cudaMalloc(&h->d_ticket, sizeof(unsigned int));
+  if (e == cudaSuccess) e = cudaMemset(h->d_ticket, 0, sizeof(unsigned int));
   if (e != cudaSuccess) { delete h; return fail(nullptr, VMB_E_NOMEM, cudaGetErrorString(e)); }
   if (hidden == 32 && n_freq == 6) {
     std::vector<int> idx(h->L.P);
@@ -126,6 +129,7 @@ void vmb_destroy(vmb_handle* h) {
   cudaSetDevice(h->device);
   if (h->d_counts) cudaFree(h->d_counts);
   if (h->d_img_index) cudaFree(h->d_img_index);
+  if (h->d_ticket) cudaFree(h->d_ticket);
   delete h;
 }
 
@@ -204,7 +208,7 @@ int vmb_forward(vmb_handle* h, const vmb_forward_args* a, void* stream) {
 }
 
 int vmb_adam(vmb_handle* h, const vmb_adam_args* a, void* stream) {
-  if (!h || !a || a->n_obj <= 0 || a->n_obj > h->max_obj || a->step < 1 || !a->params || !a->grads ||
+  if (!h || !a || a->n_obj <= 0 || a->n_obj > h->max_obj || (a->step < 1 && !a->step_counter) || !a->params || !a->grads ||
       !a->exp_avg || !a->exp_avg_sq)
     return fail(h, VMB_E_ARG, "vmb_adam: bad arguments");
   if (a->image && !h->umma_ok) return fail(h, VMB_E_UNSUPPORTED, "vmb_adam: no fp16 image for this hidden size");
@@ -220,8 +224,10 @@ int vmb_adam(vmb_handle* h, const vmb_adam_args* a, void* stream) {
   p.one_m_b1 = (float)(1.0 - b1);
   p.b2 = (float)b2;
   p.one_m_b2 = (float)(1.0 - b2);
-  const double bc1 = 1.0 - std::pow(b1, (double)a->step);
-  const double bc2 = 1.0 - std::pow(b2, (double)a->step);
+  const double tstep = (double)(a->step < 1 ? 1 : a->step);
+  const double bc1 = 1.0 - std::pow(b1, tstep);
+  const double bc2 = 1.0 - std::pow(b2, tstep);
+  p.step_counter = a->step_counter; p.ticket = h->d_ticket; p.lr = lr; p.b1 = b1; p.b2d = b2;
   p.step_size = (float)(lr / bc1);
   p.bc2_sqrt = (float)std::sqrt(bc2);
   p.eps = a->eps;

@@ -65,6 +65,7 @@ class VmapEnsemble:
         self.loss_terms = torch.zeros(n_obj, 4, **f32)
         self.status = torch.zeros(4, dtype=torch.int32, device=dev)
         self.step_count = 0
+        self.step_counter = torch.zeros(1, dtype=torch.int32, device=dev)   # device copy (graph replay)
 
     def __del__(self):
         try:
@@ -97,6 +98,7 @@ class VmapEnsemble:
     def reset_optimizer(self):
         self.exp_avg.zero_(); self.exp_avg_sq.zero_(); self.grads.zero_()
         self.step_count = 0
+        self.step_counter.zero_()
 
     def refresh_image(self):
         if self.image is not None:
@@ -159,11 +161,14 @@ class VmapEnsemble:
                 _ptr(md), md.stride(0) if B > 1 else R, _ptr(out), _stream()), "vmb_mask_counts")
         return out
 
-    def adam_step(self, guard_loss: bool = True):
-        """K2: AdamW over the whole block + zero_grad (+ fp16 image refresh)."""
+    def adam_step(self, guard_loss: bool = True, device_counter: bool = True):
+        """K2: AdamW over the whole block + zero_grad (+ fp16 image refresh).  With
+        ``device_counter`` the step number lives on the device (incremented by the kernel),
+        which is what makes a captured CUDA graph of the step replayable."""
         self.step_count += 1
         a = _lib.AdamArgs()
-        a.n_obj, a.step = self.n_obj, self.step_count
+        a.n_obj, a.step = self.n_obj, (0 if device_counter else self.step_count)
+        a.step_counter = _ptr(self.step_counter) if device_counter else None
         a.params, a.grads = _ptr(self.params), _ptr(self.grads)
         a.exp_avg, a.exp_avg_sq = _ptr(self.exp_avg), _ptr(self.exp_avg_sq)
         a.image = _ptr(self.image)
@@ -179,6 +184,19 @@ class VmapEnsemble:
         self.forward_backward(batch, impl=impl)
         self.adam_step()
         return self.loss_terms[:, 3].sum()
+
+    def capture_step(self, batch, impl: Optional[str] = None) -> "torch.cuda.CUDAGraph":
+        """Capture K0+K1+K2 on ``batch``'s (fixed) buffers into a CUDA graph; refill the buffers
+        and ``replay()`` for every step.  Removes the per-launch host overhead of the loop."""
+        self.forward_backward(batch, impl=impl, backward=False)      # warm-up: sets kernel attributes
+        torch.cuda.synchronize(self.device)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self.forward_backward(batch, impl=impl)
+            self.adam_step()
+        self.step_count -= 1                                          # capture does not execute
+        self._graph_batch = batch
+        return g
 
     def render(self, batch, impl: Optional[str] = None):
         """Forward + render only: (depth [B,R], var [B,R], colour [B,R,3], opacity [B,R])."""
@@ -212,3 +230,38 @@ class VmapEnsemble:
             raise LossExplode("loss explode (a per-object loss term exceeded 1e5); update skipped")
         if st & _lib.VMB_ST_NONFINITE:
             raise LossExplode("non-finite loss; update skipped")
+
+
+class StepInputs:
+    """One flat byte buffer holding the six input tensors of a step, so that a step's inputs
+    move host->device with a single copy (pinned twin on the host side)."""
+
+    FIELDS = (("pcs", torch.float32, lambda B, R, S: (B, R, S, 3)), ("z", torch.float32, lambda B, R, S: (B, R, S)),
+              ("gt_depth", torch.float32, lambda B, R, S: (B, R)), ("gt_colour", torch.float32, lambda B, R, S: (B, R, 3)),
+              ("sem", torch.uint8, lambda B, R, S: (B, R)), ("mask_depth", torch.uint8, lambda B, R, S: (B, R)))
+
+    def __init__(self, n_obj: int, n_rays: int, n_samples: int, device="cpu", pinned: bool = False):
+        off, spans = 0, []
+        for name, dt, shp in self.FIELDS:
+            shape = shp(n_obj, n_rays, n_samples)
+            nbytes = torch.empty((), dtype=dt).element_size()
+            for d in shape:
+                nbytes *= d
+            spans.append((name, dt, shape, off, nbytes))
+            off = (off + nbytes + 255) // 256 * 256
+        self.nbytes = off
+        self.flat = torch.empty(off, dtype=torch.uint8, device=device)
+        if pinned:
+            self.flat = self.flat.pin_memory()
+        self.views: Dict[str, torch.Tensor] = {
+            name: self.flat[o:o + n].view(dt).view(shape) for name, dt, shape, o, n in spans}
+        self.payload_bytes = sum(n for *_, n in spans)
+
+    def fill(self, batch: Dict[str, torch.Tensor]):
+        for k, v in self.views.items():
+            v.copy_(batch[k].to(v.dtype))
+        return self
+
+    def copy_from(self, other: "StepInputs", non_blocking: bool = True):
+        self.flat.copy_(other.flat, non_blocking=non_blocking)
+        return self
