@@ -39,7 +39,7 @@
 namespace um {
 
 constexpr int GT = 256;                  // threads per point group
-constexpr int NT = 2 * GT + 32;           // + the MMA issuer warp
+constexpr int NT = 2 * GT + 64;           // + one MMA issuer warp per group
 constexpr int FGB = 2048;                 // bytes of one 8-feature group for 128 points
 // feature-group index of each block inside a group's activation region
 constexpr int FG_HC = 0, FG_DH = 4, FG_FC1 = 6, FG_FC2 = 10, FG_E1 = 14, FG_FC3 = 26, FG_FC4 = 30, FG_E2 = 34;
@@ -184,24 +184,28 @@ struct Misc {
   int abort_flag;
 };
 
-// ---- the MMA issuer: one thread issues every tcgen05.mma of the CTA ---------------------
+// ---- the MMA issuer: one elected lane of a converged warp issues a group's tcgen05.mma ------
 struct Issuer {
-  uint32_t act[2], W, tm;
-  uint32_t wg_started;      // bit per wgrad accumulator: 0 -> first MMA overwrites
+  uint32_t a16, w16, tm;      // (activation base, weight base) >> 4, TMEM base
 
-  // descriptors
-  __device__ __forceinline__ uint64_t a_k(int g, int fg, int ks) const { return ptx::smem_desc(act[g] + fg * FGB + ks * 4096, 2048, 128); }
-  __device__ __forceinline__ uint64_t x_mn(int g, int fg, int ks) const { return ptx::smem_desc(act[g] + fg * FGB + ks * 256, 128, 2048); }
-  __device__ __forceinline__ uint64_t w_k(int off, int ks) const { return ptx::smem_desc(W + off + ks * 1024, 512, 128); }
-  __device__ __forceinline__ uint64_t w16_k(int off, int ks) const { return ptx::smem_desc(W + off + ks * 512, 256, 128); }
-  __device__ __forceinline__ uint64_t w_mn(int off, int ks) const { return ptx::smem_desc(W + off + ks * 256, 128, 512); }
-  __device__ __forceinline__ uint64_t w16_mn(int off) const { return ptx::smem_desc(W + off, 128, 256); }
+  // descriptors: lo word = start address >> 4 | (LBO >> 4) << 16, hi word = SBO >> 4 | version 1.
+  // Everything but the base is a compile-time constant, so each descriptor costs one add.
+  static __device__ __forceinline__ uint64_t mk(uint32_t base16, uint32_t off, uint32_t lbo, uint32_t sbo) {
+    const uint32_t lo = base16 + (off >> 4) + ((lbo >> 4) << 16);
+    const uint32_t hi = (sbo >> 4) | 0x4000u;
+    return ((uint64_t)hi << 32) | lo;
+  }
+  __device__ __forceinline__ uint64_t a_k(int, int fg, int ks) const { return mk(a16, fg * FGB + ks * 4096, 2048, 128); }
+  __device__ __forceinline__ uint64_t x_mn(int, int fg, int ks) const { return mk(a16, fg * FGB + ks * 256, 128, 2048); }
+  __device__ __forceinline__ uint64_t w_k(int off, int ks) const { return mk(w16, off + ks * 1024, 512, 128); }
+  __device__ __forceinline__ uint64_t w16_k(int off, int ks) const { return mk(w16, off + ks * 512, 256, 128); }
+  __device__ __forceinline__ uint64_t w_mn(int off, int ks) const { return mk(w16, off + ks * 256, 128, 512); }
+  __device__ __forceinline__ uint64_t w16_mn(int off) const { return mk(w16, off, 128, 256); }
 
-  __device__ __forceinline__ void wgrad(int g, int col, int bit, int fgA, int fgB, uint32_t idesc) {
-    uint32_t acc = (wg_started >> bit) & 1u;
+  // the wgrad accumulators are zeroed with tcgen05.st at segment boundaries, so every wgrad MMA accumulates
+  __device__ __forceinline__ void wgrad(int g, int col, int, int fgA, int fgB, uint32_t idesc) {
 #pragma unroll
-    for (int ks = 0; ks < 8; ++ks) { ptx::umma_f16(tm + col, x_mn(g, fgA, ks), x_mn(g, fgB, ks), idesc, acc); acc = 1u; }
-    wg_started |= 1u << bit;
+    for (int ks = 0; ks < 8; ++ks) ptx::umma_f16(tm + col, x_mn(g, fgA, ks), x_mn(g, fgB, ks), idesc, 1u);
   }
 
   __device__ __forceinline__ void stage(int g, int st) {
@@ -323,13 +327,22 @@ k_step_umma(StepParams a, VmbLayout L, const unsigned char* __restrict__ image, 
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tm = misc->tmem_base;
+  if (warp < 8) {                     // zero the persistent wgrad accumulators (192 columns x 128 lanes)
+    const uint32_t zb = tm + ((uint32_t)((warp & 3) * 32) << 16) + (warp >> 2) * 96;
+#pragma unroll
+    for (int c = 0; c < 6; ++c) ptx::tmem_st_zero16(zb + c * 16);
+    ptx::tmem_st_wait();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
 
   // this CTA's range of global tiles (tile = nr whole rays of one object)
   const long long gt_begin = (T * blockIdx.x) / gridDim.x, gt_end = (T * (blockIdx.x + 1)) / gridDim.x;
   const int n_stage = a.backward ? 12 : 6;
   uint32_t wpar = 0;                  // weight-barrier parity (one completion per segment)
   uint32_t ph = 0;                    // req/done parity of this thread's group
-  uint32_t iph[2] = {0u, 0u};         // issuer's view of the two groups' parities
+  uint32_t iph = 0;                   // issuer warp's view of its group's parity
 
   for (long long gt = gt_begin; gt < gt_end;) {
     const int b = (int)(gt / tpo);
@@ -345,28 +358,25 @@ k_step_umma(StepParams a, VmbLayout L, const unsigned char* __restrict__ image, 
     mbar_wait_or_trap(&misc->wbar, wpar);
     wpar ^= 1;
 
-    if (warp == 16) {
-      // =========================== MMA issuer ===========================================
-      if (tid == 2 * GT) {
-        Issuer is;
-        is.act[0] = ptx::smem_u32(smem + SM_ACT0); is.act[1] = ptx::smem_u32(smem + SM_ACT1);
-        is.W = ptx::smem_u32(smem + SM_W); is.tm = tm; is.wg_started = 0;
-        int left[2], st[2] = {0, 0};
-        left[0] = (t1 - t0 + 1) / 2; left[1] = (t1 - t0) / 2;
-        uint32_t spins = 0;
-        while (left[0] > 0 || left[1] > 0) {
-          if (++spins > 4000000000u) __trap();
-#pragma unroll
-          for (int g = 0; g < 2; ++g) {
-            if (left[g] > 0 && mbar_test(&misc->req[g], iph[g])) {
-              ptx::tc_fence_after();
-              is.stage(g, st[g]);
-              ptx::umma_commit(&misc->done[g]);
-              iph[g] ^= 1;
-              if (++st[g] == n_stage) { st[g] = 0; --left[g]; }
-              spins = 0;
-            }
+    if (warp >= 16) {
+      // =========================== MMA issuer of group (warp - 16) ========================
+      const int g = warp - 16;
+      Issuer is;
+      is.a16 = ptx::smem_u32(smem + (g ? SM_ACT1 : SM_ACT0)) >> 4;
+      is.w16 = ptx::smem_u32(smem + SM_W) >> 4;
+      is.tm = tm;
+      const int n_tiles = (t1 - t0 + 1 - g) / 2;
+      for (int i = 0; i < n_tiles; ++i) {
+#pragma unroll 1
+        for (int st = 0; st < n_stage; ++st) {
+          mbar_wait_or_trap(&misc->req[g], iph);
+          iph ^= 1;
+          ptx::tc_fence_after();
+          if (ptx::elect_one()) {
+            is.stage(g, st);
+            ptx::umma_commit(&misc->done[g]);
           }
+          __syncwarp();
         }
       }
     } else {
@@ -669,7 +679,10 @@ k_step_umma(StepParams a, VmbLayout L, const unsigned char* __restrict__ image, 
           const int idx = wg_target(L, blk, lane, j);
           if (idx >= 0) atomicAdd(G + idx, v[j] * INV_LS);
         }
+        ptx::tmem_st_zero16(tm + ((uint32_t)(q * 32) << 16) + blk * 32);       // ready for the next object
+        ptx::tmem_st_zero16(tm + ((uint32_t)(q * 32) << 16) + blk * 32 + 16);
       }
+      ptx::tmem_st_wait();
     }
     ptx::tc_fence_before();
     __syncthreads();
