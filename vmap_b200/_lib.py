@@ -11,7 +11,7 @@ import subprocess
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libvmap_b200.so")
+LIB_PATH = os.environ.get("VMB_LIB") or os.path.join(_HERE, "libvmap_b200.so")   # VMB_LIB: profiling variants
 CSRC = os.path.join(_HERE, "csrc")
 
 VMB_IMPL = {"auto": 0, "fp32": 1, "umma": 2}

@@ -36,6 +36,15 @@
 
 #define UMMA_MAX_S 16
 
+// Optional cycle trace (bring-up / profiling builds only: -DVMB_TRACE): CTA 0 records clock64()
+// at every stage boundary of its first tiles into a global buffer (see tools/trace_umma.py).
+#ifdef VMB_TRACE
+__device__ long long g_vmb_trace[4][256];
+#define TR(row, slot) do { if (blockIdx.x == 0 && (slot) < 256) g_vmb_trace[row][slot] = clock64(); } while (0)
+#else
+#define TR(row, slot) do { } while (0)
+#endif
+
 namespace um {
 
 constexpr int GT = 256;                  // threads per point group
@@ -135,6 +144,41 @@ __device__ __forceinline__ int wg_target(const VmbLayout& L, int blk, int lane, 
 }
 
 // two floats -> packed fp16x2 (lo, hi), saturating to +-65504 instead of overflowing to inf
+// wgrad accumulator (block 0..4, lane) -> (param index of out-column 0, stride per out-column), or -1
+__device__ __forceinline__ int wg_base(const VmbLayout& L, int blk, int lane, int& ld) {
+  ld = 1;
+  switch (blk) {
+    case 0: {
+      if (lane >= 96) return -1;
+      const int j = emb1_col_to_j(lane);
+      if (j == -2) return L.o_bin;
+      if (j < 0) return -1;
+      ld = VMB_E1; return L.o_Win + j;
+    }
+    case 1:
+      if (lane < 32) { ld = 32; return L.o_Wm1 + lane; }
+      return lane == 64 ? L.o_bm1 : -1;
+    case 2: {
+      if (lane < 32) { ld = 32 + VMB_E1; return L.o_Wcat + lane; }
+      const int j = emb1_col_to_j(lane - 32);
+      if (j == -2) return L.o_bcat;
+      if (j < 0) return -1;
+      ld = 32 + VMB_E1; return L.o_Wcat + 32 + j;
+    }
+    case 3:
+      if (lane < 32) { ld = 32; return L.o_Wm2 + lane; }
+      return lane == 64 + 42 ? L.o_bm2 : -1;
+    default: {
+      if (lane < 32) { ld = 32 + L.e2; return L.o_Wcl + lane; }
+      if (lane >= 80) return -1;
+      const int j2 = emb2_col_to_j2(lane - 32);
+      if (j2 == -2) return L.o_bcl;
+      if (j2 < 0) return -1;
+      ld = 32 + L.e2; return L.o_Wcl + 32 + j2;
+    }
+  }
+}
+
 __device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
   uint32_t r;
   asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
@@ -291,6 +335,35 @@ __device__ __forceinline__ void sin_ladder(float proj, float (&s)[6]) {
     c = fmaf(-s2, s[k - 1], 1.0f);
   }
 }
+// four independent sin ladders interleaved (ILP 4)
+__device__ __forceinline__ void sin_ladder4(const float (&proj)[4], float (&s)[4][6]) {
+  float c[4];
+#pragma unroll
+  for (int d = 0; d < 4; ++d) {
+    const float r = proj[d] - 2.0f * rintf(0.5f * proj[d]);
+    s[d][0] = __sinf(VMB_PI_F * r);
+    c[d] = __cosf(VMB_PI_F * r);
+  }
+#pragma unroll
+  for (int k = 1; k < 6; ++k)
+#pragma unroll
+    for (int d = 0; d < 4; ++d) {
+      const float s2 = s[d][k - 1] + s[d][k - 1];
+      s[d][k] = s2 * c[d];
+      c[d] = fmaf(-s2, s[d][k - 1], 1.0f);
+    }
+}
+__device__ __forceinline__ void cos_ladder4(const float (&proj)[4], float (&c)[4][6]) {
+#pragma unroll
+  for (int d = 0; d < 4; ++d) {
+    const float r = proj[d] - 2.0f * rintf(0.5f * proj[d]);
+    c[d][0] = __cosf(VMB_PI_F * r);
+  }
+#pragma unroll
+  for (int k = 1; k < 6; ++k)
+#pragma unroll
+    for (int d = 0; d < 4; ++d) c[d][k] = fmaf(c[d][k - 1] + c[d][k - 1], c[d][k - 1], -1.0f);
+}
 // cos(pi 2^k x), k = 0..5
 __device__ __forceinline__ void cos_ladder(float proj, float (&c)[6]) {
   const float r = proj - 2.0f * rintf(0.5f * proj);
@@ -302,13 +375,15 @@ __device__ __forceinline__ void cos_ladder(float proj, float (&c)[6]) {
 }  // namespace um
 
 // ---------------------------------------------------------------------------------------
+template <int SC>
 __global__ void __launch_bounds__(um::NT, 1)
 k_step_umma(StepParams a, VmbLayout L, const unsigned char* __restrict__ image, int tpo, int nr, long long T) {
   using namespace um;
   extern __shared__ __align__(1024) unsigned char smem[];
   Misc* misc = reinterpret_cast<Misc*>(smem + SM_MISC);
   const int tid = threadIdx.x, warp = tid >> 5;
-  const int S = a.S, R = a.R;
+  const int S = SC ? SC : a.S, R = a.R;      // SC: compile-time samples/ray (unrolls the render scans)
+  if (tid == 0) TR(1, 199);       // kernel entry
 
   if (tid == 0) {
     ptx::mbar_init(&misc->req[0], GT); ptx::mbar_init(&misc->req[1], GT);
@@ -335,6 +410,7 @@ k_step_umma(StepParams a, VmbLayout L, const unsigned char* __restrict__ image, 
   }
   ptx::tc_fence_before();
   __syncthreads();
+  if (tid == 0) TR(1, 200);     // setup done
   ptx::tc_fence_after();
 
   // this CTA's range of global tiles (tile = nr whole rays of one object)
@@ -356,6 +432,7 @@ k_step_umma(StepParams a, VmbLayout L, const unsigned char* __restrict__ image, 
       ptx::bulk_g2s(smem + SM_W, image + (size_t)b * IMG_BYTES, IMG_BYTES, &misc->wbar);
     }
     mbar_wait_or_trap(&misc->wbar, wpar);
+    if (tid == 0) TR(1, 201);   // segment: weights landed
     wpar ^= 1;
 
     if (warp >= 16) {
@@ -373,8 +450,10 @@ k_step_umma(StepParams a, VmbLayout L, const unsigned char* __restrict__ image, 
           iph ^= 1;
           ptx::tc_fence_after();
           if (ptx::elect_one()) {
+            TR(2 + g, (i * 12 + st) * 2);
             is.stage(g, st);
             ptx::umma_commit(&misc->done[g]);
+            TR(2 + g, (i * 12 + st) * 2 + 1);
           }
           __syncwarp();
         }
@@ -466,8 +545,11 @@ k_step_umma(StepParams a, VmbLayout L, const unsigned char* __restrict__ image, 
       };
       prefetch(t0 + g);
 
+      int trs = 0;
+#define TRG() do { if (tg == 0) { TR(g, trs); ++trs; } } while (0)
       for (int t = t0 + g; t < t1; t += 2) {
         const int r0 = t * nr;
+        TRG();                                      // tile start
         // ---- E0: positional embedding (embedding.py:82-91) ------------------------------
         const float t0x = nx * isc, t1x = ny * isc, t2x = nz * isc, zv = nzv;
         const float gd = n_gd, gc0 = n_c0, gc1 = n_c1, gc2 = n_c2;
@@ -483,15 +565,13 @@ k_step_umma(StepParams a, VmbLayout L, const unsigned char* __restrict__ image, 
 #pragma unroll 1
           for (int q = q0; q < q1; ++q) {              // directions 4q .. 4q+3
             const float* bq = Bd + q * 12;
-            float sa[6], sb[6];
-            sin_ladder(fmaf(bq[2], t2x, fmaf(bq[1], t1x, bq[0] * t0x)), sa);
-            sin_ladder(fmaf(bq[5], t2x, fmaf(bq[4], t1x, bq[3] * t0x)), sb);
-            e1[(2 * q + 1) * 128] = make_uint4(pack_h2(sa[0], sa[1]), pack_h2(sa[2], sa[3]), pack_h2(sb[0], sb[1]), pack_h2(sb[2], sb[3]));
-            const uint32_t h0 = pack_h2(sa[4], sa[5]), h1 = pack_h2(sb[4], sb[5]);
-            sin_ladder(fmaf(bq[8], t2x, fmaf(bq[7], t1x, bq[6] * t0x)), sa);
-            sin_ladder(fmaf(bq[11], t2x, fmaf(bq[10], t1x, bq[9] * t0x)), sb);
-            e1[(2 * q + 2) * 128] = make_uint4(pack_h2(sa[0], sa[1]), pack_h2(sa[2], sa[3]), pack_h2(sb[0], sb[1]), pack_h2(sb[2], sb[3]));
-            e2[q * 128] = make_uint4(h0, h1, pack_h2(sa[4], sa[5]), pack_h2(sb[4], sb[5]));
+            float pj[4], sv[4][6];
+#pragma unroll
+            for (int dd = 0; dd < 4; ++dd) pj[dd] = fmaf(bq[dd * 3 + 2], t2x, fmaf(bq[dd * 3 + 1], t1x, bq[dd * 3] * t0x));
+            sin_ladder4(pj, sv);
+            e1[(2 * q + 1) * 128] = make_uint4(pack_h2(sv[0][0], sv[0][1]), pack_h2(sv[0][2], sv[0][3]), pack_h2(sv[1][0], sv[1][1]), pack_h2(sv[1][2], sv[1][3]));
+            e1[(2 * q + 2) * 128] = make_uint4(pack_h2(sv[2][0], sv[2][1]), pack_h2(sv[2][2], sv[2][3]), pack_h2(sv[3][0], sv[3][1]), pack_h2(sv[3][2], sv[3][3]));
+            e2[q * 128] = make_uint4(pack_h2(sv[0][4], sv[0][5]), pack_h2(sv[1][4], sv[1][5]), pack_h2(sv[2][4], sv[2][5]), pack_h2(sv[3][4], sv[3][5]));
           }
           if (hsel) {
             // direction 20 shares chunk 0 of emb1 with [1, x, y, z] and chunk 5 of emb2 with the const-1 column
@@ -506,16 +586,27 @@ k_step_umma(StepParams a, VmbLayout L, const unsigned char* __restrict__ image, 
           }
         }
         STAGE_SYNC();                               // st0: in_layer
+        TRG();
         EPI_RELU(tA, F_BIN, FG_FC1);
+        TRG();
         STAGE_SYNC();                               // st1: mid1
+        TRG();
         EPI_RELU(tB, F_BM1, FG_FC2);
+        TRG();
         STAGE_SYNC();                               // st2: cat_layer
+        TRG();
         EPI_RELU(tA, F_BCAT, FG_FC3);
+        TRG();
         STAGE_SYNC();                               // st3: mid2
+        TRG();
         EPI_RELU(tB, F_BM2, FG_FC4);
+        TRG();
         STAGE_SYNC();                               // st4: color_linear + out_alpha
+        TRG();
         EPI_RELU(tA, F_BCL, FG_HC);
+        TRG();
         STAGE_SYNC();                               // st5: out_color
+        TRG();
         // ---- heads: alpha*10 -> sigmoid occupancy, colour sigmoid (model.py:77,83; render_rays.py:6)
         float occ = 0.f, c0 = 0.f, c1 = 0.f, c2 = 0.f;
         if (hsel == 0) {
@@ -527,13 +618,16 @@ k_step_umma(StepParams a, VmbLayout L, const unsigned char* __restrict__ image, 
           sc[R_OCC * 128 + p] = occ; sc[R_F * 128 + p] = 1.f - occ + 1e-10f;
           sc[R_C0 * 128 + p] = c0; sc[R_C1 * 128 + p] = c1; sc[R_C2 * 128 + p] = c2;
         }
+        TRG();
         group_bar(g);
+        TRG();
         // ---- per-ray: termination weights, rendered depth/colour/opacity, losses, ray gradients
         if (hsel == 1 && p < nr) {
           float gD = 0.f, gC0 = 0.f, gC1 = 0.f, gC2 = 0.f, gO = 0.f;
           if (smv & 0x10000) {
             const int ray = r0 + p, pb = p * S;
             float Tr = 1.f, D = 0.f, O = 0.f, C0 = 0.f, C1 = 0.f, C2 = 0.f;
+#pragma unroll
             for (int s = 0; s < S; ++s) {
               const int q = pb + s;
               const float w = sc[R_OCC * 128 + q] * Tr;                 // render_rays.py:34
@@ -543,6 +637,7 @@ k_step_umma(StepParams a, VmbLayout L, const unsigned char* __restrict__ image, 
               Tr *= sc[R_F * 128 + q];                                  // render_rays.py:29
             }
             float V = 0.f;
+#pragma unroll
             for (int s = 0; s < S; ++s) { const float dz = sc[R_Z * 128 + pb + s] - D; V = fmaf(sc[R_W * 128 + pb + s], dz * dz, V); }
             if (a.r_depth) a.r_depth[(size_t)b * R + ray] = D;
             if (a.r_var) a.r_var[(size_t)b * R + ray] = V;
@@ -562,7 +657,9 @@ k_step_umma(StepParams a, VmbLayout L, const unsigned char* __restrict__ image, 
           }
           rb[p] = gD; rb[128 + p] = gC0; rb[256 + p] = gC1; rb[384 + p] = gC2; rb[512 + p] = gO;
         }
+        TRG();
         group_bar(g);
+        TRG();
         if (!a.backward) continue;
         // ---- per-point: d(loss)/d(raw alpha, raw colour) through the termination product ---
         float Gs = 0.f, gC0 = 0.f, gC1 = 0.f, gC2 = 0.f, wq = 0.f;
@@ -583,16 +680,27 @@ k_step_umma(StepParams a, VmbLayout L, const unsigned char* __restrict__ image, 
               make_uint2(pack_h2(da, gC0 * wq * c0 * (1.f - c0)), pack_h2(gC1 * wq * c1 * (1.f - c1), gC2 * wq * c2 * (1.f - c2)));
         }
         STAGE_SYNC();                               // st6: d_hc (+ wgrad heads)
+        TRG();
         EPI_DGRAD(tA, FG_HC);
+        TRG();
         STAGE_SYNC();                               // st7: d_fc4 (+ wgrad color_linear)
+        TRG();
         EPI_DGRAD(tB, FG_FC4);
+        TRG();
         STAGE_SYNC();                               // st8: d_fc3 (+ wgrad mid2)
+        TRG();
         EPI_DGRAD(tA, FG_FC3);
+        TRG();
         STAGE_SYNC();                               // st9: d_fc2, d_emb1 part 1 (+ wgrad cat_layer)
+        TRG();
         EPI_DGRAD(tB, FG_FC2);
+        TRG();
         STAGE_SYNC();                               // st10: d_fc1 (+ wgrad mid1)
+        TRG();
         EPI_DGRAD(tA, FG_FC1);
+        TRG();
         STAGE_SYNC();                               // st11: d_emb1 part 2 -> E, d_emb2 -> A[0..48) (+ wgrad in_layer)
+        TRG();
         // ---- PE backward: dproj_d = pi * sum_k 2^k g_{k,d} cos(pi 2^k proj_d) ------------
         {
           const int q0 = hsel ? 3 : 0, q1 = hsel ? 5 : 3;
@@ -604,17 +712,19 @@ k_step_umma(StepParams a, VmbLayout L, const unsigned char* __restrict__ image, 
             tmem_ld8(tA + 8 * q, g2);                 // emb2 cols (k = 4, 5)
             ptx::tmem_ld_wait();
             const float* bq = Bd + q * 12;
+            float pj[4], cv[4][6];
+#pragma unroll
+            for (int dd = 0; dd < 4; ++dd) pj[dd] = fmaf(bq[dd * 3 + 2], t2x, fmaf(bq[dd * 3 + 1], t1x, bq[dd * 3] * t0x));
+            cos_ladder4(pj, cv);
 #pragma unroll
             for (int dd = 0; dd < 4; ++dd) {
-              float c[6];
-              cos_ladder(fmaf(bq[dd * 3 + 2], t2x, fmaf(bq[dd * 3 + 1], t1x, bq[dd * 3] * t0x)), c);
               const float* g1 = (dd < 2) ? (g1a + dd * 4) : (g1b + (dd - 2) * 4);
-              float dp = g1[0] * c[0];
-              dp = fmaf(2.f * g1[1], c[1], dp);
-              dp = fmaf(4.f * g1[2], c[2], dp);
-              dp = fmaf(8.f * g1[3], c[3], dp);
-              dp = fmaf(16.f * g2[dd * 2], c[4], dp);
-              dp = fmaf(32.f * g2[dd * 2 + 1], c[5], dp);
+              float dp = g1[0] * cv[dd][0];
+              dp = fmaf(2.f * g1[1], cv[dd][1], dp);
+              dp = fmaf(4.f * g1[2], cv[dd][2], dp);
+              dp = fmaf(8.f * g1[3], cv[dd][3], dp);
+              dp = fmaf(16.f * g2[dd * 2], cv[dd][4], dp);
+              dp = fmaf(32.f * g2[dd * 2 + 1], cv[dd][5], dp);
               dpr[(4 * q + dd) * 128 + p] = dp * VMB_PI_F;
             }
           }
@@ -630,23 +740,28 @@ k_step_umma(StepParams a, VmbLayout L, const unsigned char* __restrict__ image, 
             dpr[20 * 128 + p] = dp * VMB_PI_F;
           }
         }
+        TRG();
         ptx::tc_fence_before();
         group_bar(g);
         ptx::tc_fence_after();
-        {   // dB[d][i] += sum_p dproj[d][p] * t_i[p]  (embedding.py:84): 63 outputs x 4 point quarters
-          const int o = tg & 63, quarter = tg >> 6;
-          if (o < 63) {
+        TRG();
+        {   // dB[d][i] += sum_p dproj[d][p] * t_i[p]  (embedding.py:84): warp w owns outputs w, w+8, ...
+          const int w8 = tg >> 5, ln = tg & 31;
+#pragma unroll 1
+          for (int o = w8; o < 63; o += 8) {
             const int d = o / 3, i = o - d * 3;
-            const float* dp = dpr + d * 128 + quarter * 32;
-            const float* tp = sc + (R_T0 + i) * 128 + quarter * 32;
-            float acc = 0.f;
-#pragma unroll 8
-            for (int k = 0; k < 32; ++k) acc = fmaf(dp[k], tp[k], acc);
-            atomicAdd(&dbs[o], acc);
+            const float* dp = dpr + d * 128 + ln;
+            const float* tp = sc + (R_T0 + i) * 128 + ln;
+            float acc = dp[0] * tp[0];
+            acc = fmaf(dp[32], tp[32], acc); acc = fmaf(dp[64], tp[64], acc); acc = fmaf(dp[96], tp[96], acc);
+            acc = warp_sum(acc);
+            if (ln == 0) dbs[o] += acc;
           }
         }
         group_bar(g);                               // scratch is free for the next tile
+        TRG();
       }
+#undef TRG
 #undef STAGE_SYNC
 #undef EPI_RELU
 #undef EPI_DGRAD
@@ -663,6 +778,7 @@ k_step_umma(StepParams a, VmbLayout L, const unsigned char* __restrict__ image, 
     // ---- segment end: all MMAs have completed (each group waited on its last commit) -----
     ptx::tc_fence_before();
     __syncthreads();
+    if (tid == 0) TR(1, 202);   // segment: all tiles done, before flush
     ptx::tc_fence_after();
     if (a.backward && warp < 8) {
       // flush the wgrad accumulators: TMEM -> registers -> fp32 atomics on the grad block
@@ -674,10 +790,25 @@ k_step_umma(StepParams a, VmbLayout L, const unsigned char* __restrict__ image, 
         float v[32];
         ptx::tmem_ld32(tm + ((uint32_t)(q * 32) << 16) + blk * 32, v);
         ptx::tmem_ld_wait();
+        if (blk < 5) {
+          int ld;
+          const int base = wg_base(L, blk, lane, ld);
+          if (base >= 0) {
+            float* gp = G + base;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int idx = wg_target(L, blk, lane, j);
-          if (idx >= 0) atomicAdd(G + idx, v[j] * INV_LS);
+            for (int j = 0; j < 32; ++j) atomicAdd(gp + j * ld, v[j] * INV_LS);
+          }
+        } else {    // heads: col 0 = out_alpha, cols 17..19 = out_color rows
+          if (lane < 32) {
+            atomicAdd(G + L.o_Wa + lane, v[0] * INV_LS);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) atomicAdd(G + L.o_Woc + c * 32 + lane, v[17 + c] * INV_LS);
+          } else if (lane == 32 + 42) {
+            atomicAdd(G + L.o_ba, v[0] * INV_LS);
+          } else if (lane == 112) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) atomicAdd(G + L.o_boc + c, v[17 + c] * INV_LS);
+          }
         }
         ptx::tmem_st_zero16(tm + ((uint32_t)(q * 32) << 16) + blk * 32);       // ready for the next object
         ptx::tmem_st_zero16(tm + ((uint32_t)(q * 32) << 16) + blk * 32 + 16);
@@ -686,9 +817,11 @@ k_step_umma(StepParams a, VmbLayout L, const unsigned char* __restrict__ image, 
     }
     ptx::tc_fence_before();
     __syncthreads();
+    if (tid == 0) TR(1, 203);   // segment: after flush
     ptx::tc_fence_after();
   }
 
+  if (tid == 0) TR(1, 204);       // kernel end
   if (warp == 16) ptx::tmem_dealloc(tm, 512);
 }
 
@@ -733,7 +866,9 @@ static int umma_launch_step(const VmbLayout& L, const StepParams& sp, const void
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-    cudaError_t e = cudaFuncSetAttribute(k_step_umma, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(k_step_umma<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_step_umma<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_step_umma<14>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     if (e != cudaSuccess) { n_sm = 0; err = std::string("cudaFuncSetAttribute(k_step_umma): ") + cudaGetErrorString(e); return -2; }
   }
   const int nr = 128 / sp.S;
@@ -742,7 +877,10 @@ static int umma_launch_step(const VmbLayout& L, const StepParams& sp, const void
   long long grid = (T + 1) / 2;
   if (grid > n_sm) grid = n_sm;
   if (grid < 1) grid = 1;
-  k_step_umma<<<(unsigned)grid, NT, SMEM_BYTES, st>>>(sp, L, (const unsigned char*)image, tpo, nr, T);
+  const unsigned char* img = (const unsigned char*)image;
+  if (sp.S == 10)      k_step_umma<10><<<(unsigned)grid, NT, SMEM_BYTES, st>>>(sp, L, img, tpo, nr, T);
+  else if (sp.S == 14) k_step_umma<14><<<(unsigned)grid, NT, SMEM_BYTES, st>>>(sp, L, img, tpo, nr, T);
+  else                 k_step_umma<0><<<(unsigned)grid, NT, SMEM_BYTES, st>>>(sp, L, img, tpo, nr, T);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { err = std::string("k_step_umma launch: ") + cudaGetErrorString(e); return -2; }
   return 0;

@@ -273,4 +273,15 @@ int vmb_sample(vmb_handle* h, const vmb_sample_args* a, void* stream) {
   return VMB_OK;
 }
 
+#ifdef VMB_TRACE
+// profiling builds only: copy the kernel's cycle trace to the host (4 x 256 clock64 stamps)
+int vmb_trace_read(long long* host_out) {
+  return cudaMemcpyFromSymbol(host_out, g_vmb_trace, sizeof(long long) * 4 * 256) == cudaSuccess ? 0 : -2;
+}
+int vmb_trace_clear(void) {
+  static long long z[4 * 256];
+  return cudaMemcpyToSymbol(g_vmb_trace, z, sizeof(z)) == cudaSuccess ? 0 : -2;
+}
+#endif
+
 }  // extern "C"
