@@ -2,13 +2,13 @@
 // fp16 operands / fp32 accumulate on the 5th-gen tensor cores (tcgen05.mma, TMEM
 // accumulators), weights staged per object with one bulk async copy (TMA engine).
 //
-// CTA = 544 threads: two "point groups" of 256 threads plus one MMA-issuer warp.  A group owns
+// CTA = 512 threads: two "point groups" of 256 threads.  A group owns
 // a tile of up to 128 sample points (whole rays); two threads share a point (= one TMEM lane),
 // splitting the accumulator columns / PE directions, so the per-stage epilogue latency halves
 // and each SM sub-partition has 4 resident compute warps.  Each group walks its tile through
 // 12 MMA stages in lock-step: threads write the next operand rows to
-// shared memory, arrive on the group's request mbarrier, the issuer thread issues the
-// stage's tcgen05.mma batch and commits to the group's done mbarrier, threads read the
+// shared memory, meet at the group's named barrier, one elected lane of the group's first warp
+// issues the stage's tcgen05.mma batch and commits to the group's mbarrier, threads read the
 // accumulator back with tcgen05.ld.  The two groups run out of phase, so one group's
 // epilogue overlaps the other's MMAs.  Weight gradients accumulate in TMEM across all the
 // tiles a CTA owns for an object and are flushed once (fp32 atomics) per (CTA, object).
@@ -48,7 +48,7 @@ __device__ long long g_vmb_trace[4][256];
 namespace um {
 
 constexpr int GT = 256;                  // threads per point group
-constexpr int NT = 2 * GT + 64;           // + one MMA issuer warp per group
+constexpr int NT = 2 * GT;                // no dedicated issuer warps: warp 0 of a group issues its MMAs
 constexpr int FGB = 2048;                 // bytes of one 8-feature group for 128 points
 // feature-group index of each block inside a group's activation region
 constexpr int FG_HC = 0, FG_DH = 4, FG_FC1 = 6, FG_FC2 = 10, FG_E1 = 14, FG_FC3 = 26, FG_FC4 = 30, FG_E2 = 34;
@@ -377,7 +377,7 @@ __device__ __forceinline__ void cos_ladder(float proj, float (&c)[6]) {
 // ---------------------------------------------------------------------------------------
 template <int SC>
 __global__ void __launch_bounds__(um::NT, 1)
-k_step_umma(StepParams a, VmbLayout L, const unsigned char* __restrict__ image, int tpo, int nr, long long T) {
+k_step_umma(StepParams a, VmbLayout L, const unsigned char* __restrict__ image, int tpo, int nr, long long T, int phase_delay) {
   using namespace um;
   extern __shared__ __align__(1024) unsigned char smem[];
   Misc* misc = reinterpret_cast<Misc*>(smem + SM_MISC);
@@ -392,7 +392,7 @@ k_step_umma(StepParams a, VmbLayout L, const unsigned char* __restrict__ image, 
     misc->abort_flag = 0;
     ptx::mbar_init_fence();
   }
-  if (warp == 16) { ptx::tmem_alloc(&misc->tmem_base, 512); ptx::tmem_relinquish(); }
+  if (warp == 15) { ptx::tmem_alloc(&misc->tmem_base, 512); ptx::tmem_relinquish(); }
   if (tid < 3) {                      // render_rays.py:68-73: one empty mask anywhere zeroes the term for all
     int on = 1;
     for (int i = 0; i < a.B; ++i) on &= (a.counts[i * 4 + tid] != 0);
@@ -415,10 +415,8 @@ k_step_umma(StepParams a, VmbLayout L, const unsigned char* __restrict__ image, 
 
   // this CTA's range of global tiles (tile = nr whole rays of one object)
   const long long gt_begin = (T * blockIdx.x) / gridDim.x, gt_end = (T * (blockIdx.x + 1)) / gridDim.x;
-  const int n_stage = a.backward ? 12 : 6;
   uint32_t wpar = 0;                  // weight-barrier parity (one completion per segment)
   uint32_t ph = 0;                    // req/done parity of this thread's group
-  uint32_t iph = 0;                   // issuer warp's view of its group's parity
 
   for (long long gt = gt_begin; gt < gt_end;) {
     const int b = (int)(gt / tpo);
@@ -435,30 +433,7 @@ k_step_umma(StepParams a, VmbLayout L, const unsigned char* __restrict__ image, 
     if (tid == 0) TR(1, 201);   // segment: weights landed
     wpar ^= 1;
 
-    if (warp >= 16) {
-      // =========================== MMA issuer of group (warp - 16) ========================
-      const int g = warp - 16;
-      Issuer is;
-      is.a16 = ptx::smem_u32(smem + (g ? SM_ACT1 : SM_ACT0)) >> 4;
-      is.w16 = ptx::smem_u32(smem + SM_W) >> 4;
-      is.tm = tm;
-      const int n_tiles = (t1 - t0 + 1 - g) / 2;
-      for (int i = 0; i < n_tiles; ++i) {
-#pragma unroll 1
-        for (int st = 0; st < n_stage; ++st) {
-          mbar_wait_or_trap(&misc->req[g], iph);
-          iph ^= 1;
-          ptx::tc_fence_after();
-          if (ptx::elect_one()) {
-            TR(2 + g, (i * 12 + st) * 2);
-            is.stage(g, st);
-            ptx::umma_commit(&misc->done[g]);
-            TR(2 + g, (i * 12 + st) * 2 + 1);
-          }
-          __syncwarp();
-        }
-      }
-    } else {
+    {
       // =========================== point groups ==========================================
       const int g = warp >> 3, tg = tid & (GT - 1);
       const int p = tg & 127, hsel = tg >> 7;          // point slot (= TMEM lane), column / direction half
@@ -481,12 +456,33 @@ k_step_umma(StepParams a, VmbLayout L, const unsigned char* __restrict__ image, 
       const int rl = p / S, sidx = p - rl * S;
       if (tg < 64) dbs[tg] = 0.f;
       group_bar(g);
+      if (g == 1 && phase_delay > 0 && t0 == (int)(gt_begin - (long long)b * tpo)) {   // de-phase the two groups once
+        const long long c0 = clock64();
+        while (clock64() - c0 < phase_delay) {}
+      }
 
-#define STAGE_SYNC()                                   \
+      Issuer is;
+      is.a16 = ptx::smem_u32(act) >> 4;
+      is.w16 = ptx::smem_u32(smem + SM_W) >> 4;
+      is.tm = tm;
+      const bool issuer_warp = (warp & 7) == 0;
+      // operands written -> group barrier -> warp 0 of the group issues the stage's MMAs and commits
+      // to the group's mbarrier -> everyone waits for the accumulator
+#define STAGE_SYNC(ST)                                 \
   do {                                                 \
     ptx::fence_async_smem();                           \
     ptx::tc_fence_before();                            \
-    ptx::mbar_arrive(&misc->req[g]);                   \
+    group_bar(g);                                      \
+    if (issuer_warp) {                                 \
+      ptx::tc_fence_after();                           \
+      if (ptx::elect_one()) {                          \
+        TR(2 + g, trs2); ++trs2;                       \
+        is.stage(g, ST);                               \
+        ptx::umma_commit(&misc->done[g]);              \
+        TR(2 + g, trs2); ++trs2;                       \
+      }                                                \
+      __syncwarp();                                    \
+    }                                                  \
     mbar_wait_or_trap(&misc->done[g], ph);             \
     ph ^= 1;                                           \
     ptx::tc_fence_after();                             \
@@ -545,7 +541,7 @@ k_step_umma(StepParams a, VmbLayout L, const unsigned char* __restrict__ image, 
       };
       prefetch(t0 + g);
 
-      int trs = 0;
+      int trs = 0, trs2 = 0;
 #define TRG() do { if (tg == 0) { TR(g, trs); ++trs; } } while (0)
       for (int t = t0 + g; t < t1; t += 2) {
         const int r0 = t * nr;
@@ -585,27 +581,27 @@ k_step_umma(StepParams a, VmbLayout L, const unsigned char* __restrict__ image, 
             dh[0] = make_uint4(0u, 0u, 0u, 0u); dh[128] = make_uint4(0u, 0u, 0u, 0u);
           }
         }
-        STAGE_SYNC();                               // st0: in_layer
+        STAGE_SYNC(0);                               // st0: in_layer
         TRG();
         EPI_RELU(tA, F_BIN, FG_FC1);
         TRG();
-        STAGE_SYNC();                               // st1: mid1
+        STAGE_SYNC(1);                               // st1: mid1
         TRG();
         EPI_RELU(tB, F_BM1, FG_FC2);
         TRG();
-        STAGE_SYNC();                               // st2: cat_layer
+        STAGE_SYNC(2);                               // st2: cat_layer
         TRG();
         EPI_RELU(tA, F_BCAT, FG_FC3);
         TRG();
-        STAGE_SYNC();                               // st3: mid2
+        STAGE_SYNC(3);                               // st3: mid2
         TRG();
         EPI_RELU(tB, F_BM2, FG_FC4);
         TRG();
-        STAGE_SYNC();                               // st4: color_linear + out_alpha
+        STAGE_SYNC(4);                               // st4: color_linear + out_alpha
         TRG();
         EPI_RELU(tA, F_BCL, FG_HC);
         TRG();
-        STAGE_SYNC();                               // st5: out_color
+        STAGE_SYNC(5);                               // st5: out_color
         TRG();
         // ---- heads: alpha*10 -> sigmoid occupancy, colour sigmoid (model.py:77,83; render_rays.py:6)
         float occ = 0.f, c0 = 0.f, c1 = 0.f, c2 = 0.f;
@@ -679,27 +675,27 @@ k_step_umma(StepParams a, VmbLayout L, const unsigned char* __restrict__ image, 
           *reinterpret_cast<uint2*>(act + FG_DH * FGB + p * 16) =
               make_uint2(pack_h2(da, gC0 * wq * c0 * (1.f - c0)), pack_h2(gC1 * wq * c1 * (1.f - c1), gC2 * wq * c2 * (1.f - c2)));
         }
-        STAGE_SYNC();                               // st6: d_hc (+ wgrad heads)
+        STAGE_SYNC(6);                               // st6: d_hc (+ wgrad heads)
         TRG();
         EPI_DGRAD(tA, FG_HC);
         TRG();
-        STAGE_SYNC();                               // st7: d_fc4 (+ wgrad color_linear)
+        STAGE_SYNC(7);                               // st7: d_fc4 (+ wgrad color_linear)
         TRG();
         EPI_DGRAD(tB, FG_FC4);
         TRG();
-        STAGE_SYNC();                               // st8: d_fc3 (+ wgrad mid2)
+        STAGE_SYNC(8);                               // st8: d_fc3 (+ wgrad mid2)
         TRG();
         EPI_DGRAD(tA, FG_FC3);
         TRG();
-        STAGE_SYNC();                               // st9: d_fc2, d_emb1 part 1 (+ wgrad cat_layer)
+        STAGE_SYNC(9);                               // st9: d_fc2, d_emb1 part 1 (+ wgrad cat_layer)
         TRG();
         EPI_DGRAD(tB, FG_FC2);
         TRG();
-        STAGE_SYNC();                               // st10: d_fc1 (+ wgrad mid1)
+        STAGE_SYNC(10);                               // st10: d_fc1 (+ wgrad mid1)
         TRG();
         EPI_DGRAD(tA, FG_FC1);
         TRG();
-        STAGE_SYNC();                               // st11: d_emb1 part 2 -> E, d_emb2 -> A[0..48) (+ wgrad in_layer)
+        STAGE_SYNC(11);                               // st11: d_emb1 part 2 -> E, d_emb2 -> A[0..48) (+ wgrad in_layer)
         TRG();
         // ---- PE backward: dproj_d = pi * sum_k 2^k g_{k,d} cos(pi 2^k proj_d) ------------
         {
@@ -747,15 +743,26 @@ k_step_umma(StepParams a, VmbLayout L, const unsigned char* __restrict__ image, 
         TRG();
         {   // dB[d][i] += sum_p dproj[d][p] * t_i[p]  (embedding.py:84): warp w owns outputs w, w+8, ...
           const int w8 = tg >> 5, ln = tg & 31;
-#pragma unroll 1
-          for (int o = w8; o < 63; o += 8) {
+          float acc[8];
+#pragma unroll
+          for (int i8 = 0; i8 < 8; ++i8) {           // 8 independent dot products per warp (ILP)
+            const int o = min(w8 + 8 * i8, 62);
             const int d = o / 3, i = o - d * 3;
             const float* dp = dpr + d * 128 + ln;
             const float* tp = sc + (R_T0 + i) * 128 + ln;
-            float acc = dp[0] * tp[0];
-            acc = fmaf(dp[32], tp[32], acc); acc = fmaf(dp[64], tp[64], acc); acc = fmaf(dp[96], tp[96], acc);
-            acc = warp_sum(acc);
-            if (ln == 0) dbs[o] += acc;
+            float v = dp[0] * tp[0];
+            v = fmaf(dp[32], tp[32], v); v = fmaf(dp[64], tp[64], v); v = fmaf(dp[96], tp[96], v);
+            acc[i8] = v;
+          }
+#pragma unroll
+          for (int sft = 16; sft > 0; sft >>= 1)
+#pragma unroll
+            for (int i8 = 0; i8 < 8; ++i8) acc[i8] += __shfl_xor_sync(0xffffffffu, acc[i8], sft);
+          if (ln < 8 && w8 + 8 * ln < 63) {
+            float v = acc[0];
+#pragma unroll
+            for (int i8 = 1; i8 < 8; ++i8) v = (ln == i8) ? acc[i8] : v;
+            dbs[w8 + 8 * ln] += v;
           }
         }
         group_bar(g);                               // scratch is free for the next tile
@@ -822,7 +829,7 @@ k_step_umma(StepParams a, VmbLayout L, const unsigned char* __restrict__ image, 
   }
 
   if (tid == 0) TR(1, 204);       // kernel end
-  if (warp == 16) ptx::tmem_dealloc(tm, 512);
+  if (warp == 15) ptx::tmem_dealloc(tm, 512);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -878,9 +885,11 @@ static int umma_launch_step(const VmbLayout& L, const StepParams& sp, const void
   if (grid > n_sm) grid = n_sm;
   if (grid < 1) grid = 1;
   const unsigned char* img = (const unsigned char*)image;
-  if (sp.S == 10)      k_step_umma<10><<<(unsigned)grid, NT, SMEM_BYTES, st>>>(sp, L, img, tpo, nr, T);
-  else if (sp.S == 14) k_step_umma<14><<<(unsigned)grid, NT, SMEM_BYTES, st>>>(sp, L, img, tpo, nr, T);
-  else                 k_step_umma<0><<<(unsigned)grid, NT, SMEM_BYTES, st>>>(sp, L, img, tpo, nr, T);
+  static int phase_delay = -1;
+  if (phase_delay < 0) { const char* e = getenv("VMB_PHASE_DELAY"); phase_delay = e ? atoi(e) : 0; }   // experiment knob: cycles by which group 1 is de-phased at start
+  if (sp.S == 10)      k_step_umma<10><<<(unsigned)grid, NT, SMEM_BYTES, st>>>(sp, L, img, tpo, nr, T, phase_delay);
+  else if (sp.S == 14) k_step_umma<14><<<(unsigned)grid, NT, SMEM_BYTES, st>>>(sp, L, img, tpo, nr, T, phase_delay);
+  else                 k_step_umma<0><<<(unsigned)grid, NT, SMEM_BYTES, st>>>(sp, L, img, tpo, nr, T, phase_delay);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { err = std::string("k_step_umma launch: ") + cudaGetErrorString(e); return -2; }
   return 0;
