@@ -29,6 +29,22 @@ FLOP_PER_POINT = 6 * (4 * HIDDEN * HIDDEN + 220 * HIDDEN + 63)      # SURVEY.md 
 METRIC = "training-step rays/sec at n_obj x n_rays x n_samples"
 
 
+def k1_dram_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of one K1 launch from the committed ncu summary."""
+    f = os.path.join(ROOT, "profiles", "r01_k_step_umma_ncu_summary.txt")
+    if not os.path.isfile(f):
+        return None
+    tot, seen = 0.0, 0
+    mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    for ln in open(f):
+        for key in ("dram__bytes_read.sum [", "dram__bytes_write.sum ["):
+            if ln.startswith(key):
+                unit = ln[len(key):ln.index("]")]
+                tot += float(ln.split("=")[1]) * mult.get(unit, 1.0)
+                seen += 1
+    return tot if seen == 2 else None
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.isfile(p):
@@ -279,7 +295,7 @@ def run_ours(args):
                     "pipeline": "double-buffered staging: H2D of step i+1 on a copy stream overlaps step i"},
             "gpu_launches": 3 * K,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": bf16_burst, "unit": "TFLOP/s",
-                         "frac": achieved / bf16_burst, "traffic": None, "peak_source": src + " bf16 burst",
+                         "frac": achieved / bf16_burst, "traffic": k1_dram_traffic() if impl in ("auto", "umma") and world == 1 else None, "peak_source": src + " bf16 burst",
                          "peak_sustained": bf16_sust, "kernel": "k_step_umma" if impl in ("auto", "umma") else "k_step_fp32",
                          "kernel_us": k1_avg_ms * 1e3, "kernel_us_median": k1_ms[len(k1_ms) // 2] * 1e3,
                          "flop_per_launch": flop_k1,
