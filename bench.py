@@ -169,6 +169,9 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     impl = os.environ.get("VMB_IMPL", "auto")
 
+    sampler = ClockSampler(local)                 # runs for the whole process; windowed to the timed arms below
+    if rank == 0:
+        sampler.start()
     B, R, S = N_OBJ, N_RAYS, N_SAMPLES            # per GPU (weak scaling)
     params = vo.init_params(B, HIDDEN, seed=1000 + rank)
     ens = VmapEnsemble(B, hidden=HIDDEN, scale=2.0, device=dev, impl=impl)
@@ -214,10 +217,6 @@ def run_ours(args):
             ens.forward_backward(pool[i].views)
             ens.adam_step()
 
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-
     # ---- device-resident arm ("value"): inputs already in HBM ---------------------------------
     for i in range(W):
         run_step(i % n_pool, dev_pool, pool_graphs if use_graphs else None)
@@ -241,7 +240,6 @@ def run_ours(args):
     barrier()
     k1_ms = sorted(a.elapsed_time(b) for a, b in k1_events)
     k1_avg_ms = sum(k1_ms) / len(k1_ms)
-    clocks = sampler.stop(t_wall0, time.time()) if rank == 0 else None
 
     # ---- end-to-end arm: pinned host inputs -> H2D -> step -> D2H loss terms --------------------
     # double-buffered: the copy of step i+1's inputs (copy stream) overlaps step i's kernels.
@@ -271,6 +269,12 @@ def run_ours(args):
     e2e_ms = max_over_ranks(f0.elapsed_time(f1))
     ens.check_status()
     assert bool(torch.isfinite(loss_host).all())
+    # keep the GPU under the same load a little longer so that nvidia-smi (>= 50 ms period) sees it
+    t_hold = time.time()
+    while time.time() - t_hold < 0.35:
+        e2e_loop(50, 0)
+        torch.cuda.synchronize()
+    clocks = sampler.stop(t_wall0, time.time()) if rank == 0 else None
 
     if rank == 0:
         bf16_burst, bf16_sust, hbm, src = peaks()

@@ -29,7 +29,7 @@ for g in range(2):
     t = buf[g]
     n = int((t != 0).sum())
     print(f"--- group {g}: {n} stamps; per-tile stamps = 30")
-    per = 30
+    per = int(os.environ.get('TRACE_PER', 30))
     for tile in range(min(3, n // per)):
         seg = t[tile * per:(tile + 1) * per + 1]
         d = np.diff(seg)
