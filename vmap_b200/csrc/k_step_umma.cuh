@@ -9,8 +9,8 @@
 // 12 MMA stages in lock-step: threads write the next operand rows to
 // shared memory, meet at the group's named barrier, one elected lane of the group's first warp
 // issues the stage's tcgen05.mma batch and commits to the group's mbarrier, threads read the
-// accumulator back with tcgen05.ld.  The two groups run out of phase, so one group's
-// epilogue overlaps the other's MMAs.  Weight gradients accumulate in TMEM across all the
+// accumulator back with tcgen05.ld.  The two groups are independent, so one group's epilogue
+// can overlap the other's MMAs.  Weight gradients accumulate in TMEM across all the
 // tiles a CTA owns for an object and are flushed once (fp32 atomics) per (CTA, object).
 //
 // Shared-memory operand layout: SWIZZLE_NONE 8x8 core matrices.  An activation block is
@@ -108,42 +108,6 @@ __host__ __device__ inline int j2_to_emb2_col(int j2) {
 __host__ __device__ inline int widx32(int base_bytes, int o, int c) { return (base_bytes + (c >> 3) * 512 + o * 16 + (c & 7) * 2) >> 1; }
 __host__ __device__ inline int widx16(int base_bytes, int j, int o) { return (base_bytes + (o >> 3) * 256 + j * 16 + (o & 7) * 2) >> 1; }
 
-// wgrad accumulator (block, lane, out col) -> param index (or -1)
-__device__ __forceinline__ int wg_target(const VmbLayout& L, int blk, int lane, int o) {
-  switch (blk) {
-    case 0: {   // in_layer: lanes = emb1 cols
-      if (lane >= 96) return -1;
-      const int j = emb1_col_to_j(lane);
-      return j == -2 ? L.o_bin + o : (j < 0 ? -1 : L.o_Win + o * VMB_E1 + j);
-    }
-    case 1:     // mid1: lanes = fc1 | fc2 | emb1[0..64)
-      return lane < 32 ? L.o_Wm1 + o * 32 + lane : (lane == 64 ? L.o_bm1 + o : -1);
-    case 2: {   // cat_layer: lanes = fc2 | emb1
-      if (lane < 32) return L.o_Wcat + o * (32 + VMB_E1) + lane;
-      const int j = emb1_col_to_j(lane - 32);
-      return j == -2 ? L.o_bcat + o : (j < 0 ? -1 : L.o_Wcat + o * (32 + VMB_E1) + 32 + j);
-    }
-    case 3:     // mid2: lanes = fc3 | fc4 | emb2
-      return lane < 32 ? L.o_Wm2 + o * 32 + lane : (lane == 64 + 42 ? L.o_bm2 + o : -1);
-    case 4: {   // color_linear: lanes = fc4 | emb2
-      if (lane < 32) return L.o_Wcl + o * (32 + L.e2) + lane;
-      if (lane >= 80) return -1;
-      const int j2 = emb2_col_to_j2(lane - 32);
-      return j2 == -2 ? L.o_bcl + o : (j2 < 0 ? -1 : L.o_Wcl + o * (32 + L.e2) + 32 + j2);
-    }
-    default: {  // heads: cols 0..15 = WG_A (A = fc4 | emb2), cols 16..31 = WG_OC (A = hc | dh | fc1 | fc2 | emb1[0..16))
-      if (o < 16) {
-        if (o != 0) return -1;
-        return lane < 32 ? L.o_Wa + lane : (lane == 32 + 42 ? L.o_ba : -1);
-      }
-      const int c = o - 16;
-      if (c < 1 || c > 3) return -1;
-      return lane < 32 ? L.o_Woc + (c - 1) * 32 + lane : (lane == 112 ? L.o_boc + c - 1 : -1);
-    }
-  }
-}
-
-// two floats -> packed fp16x2 (lo, hi), saturating to +-65504 instead of overflowing to inf
 // wgrad accumulator (block 0..4, lane) -> (param index of out-column 0, stride per out-column), or -1
 __device__ __forceinline__ int wg_base(const VmbLayout& L, int blk, int lane, int& ld) {
   ld = 1;
@@ -224,7 +188,7 @@ __device__ __forceinline__ void mbar_wait_or_trap(uint64_t* bar, uint32_t parity
 __device__ __forceinline__ void group_bar(int g) { asm volatile("bar.sync %0, 256;" ::"r"(1 + g) : "memory"); }
 
 struct Misc {
-  uint64_t req[2], done[2], wbar;
+  uint64_t done[2], wbar;
   uint32_t tmem_base;
   int on[3];
   int abort_flag;
@@ -388,7 +352,6 @@ k_step_umma(StepParams a, VmbLayout L, const unsigned char* __restrict__ image, 
   if (tid == 0) TR(1, 199);       // kernel entry
 
   if (tid == 0) {
-    ptx::mbar_init(&misc->req[0], GT); ptx::mbar_init(&misc->req[1], GT);
     ptx::mbar_init(&misc->done[0], 1);  ptx::mbar_init(&misc->done[1], 1);
     ptx::mbar_init(&misc->wbar, 1);
     misc->abort_flag = 0;
