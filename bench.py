@@ -155,7 +155,7 @@ def run_reference(args):
 def run_ours(args):
     import torch
     import torch.distributed as dist
-    from oracle import vmap_oracle as vo          # input generator + cpu_baseline leg only
+    from vmap_b200 import synth as vo             # product-side input generator (oracle/ is only used by the cpu legs)
     from vmap_b200.ensemble import VmapEnsemble
 
     world = int(os.environ.get("WORLD_SIZE", "1"))

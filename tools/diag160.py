@@ -1,7 +1,7 @@
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from oracle import vmap_oracle as vo
+from vmap_b200 import synth as vo
 from vmap_b200.ensemble import VmapEnsemble
 n_obj, R, S = 160, 240, 10
 params = vo.init_params(n_obj, 32, seed=2)

@@ -4,7 +4,7 @@ steps of one frame (train.py:195-326), shipped vMAP shape (120 rays/step) and th
 import json, os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from oracle import vmap_oracle as vo
+from vmap_b200 import synth as vo
 from oracle import sampler_oracle as so
 from vmap_b200.ensemble import VmapEnsemble
 from vmap_b200.sampler import BatchedSampler, KeyframeSet

@@ -5,7 +5,7 @@ import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import torch.distributed as dist
-from oracle import vmap_oracle as vo
+from vmap_b200 import synth as vo
 from vmap_b200.dist import ReplicatedStep, shard_objects
 from vmap_b200.ensemble import VmapEnsemble
 

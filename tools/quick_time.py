@@ -2,7 +2,7 @@
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from oracle import vmap_oracle as vo
+from vmap_b200 import synth as vo
 from vmap_b200.ensemble import VmapEnsemble
 
 B, R, S = int(os.environ.get("B", 20)), int(os.environ.get("R", 1200)), int(os.environ.get("S", 10))

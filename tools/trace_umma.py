@@ -3,7 +3,7 @@ Usage: VMB_LIB=vmap_b200/libvmap_b200_trace.so python tools/trace_umma.py"""
 import ctypes as C, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
-from oracle import vmap_oracle as vo
+from vmap_b200 import synth as vo
 from vmap_b200 import _lib
 from vmap_b200.ensemble import VmapEnsemble
 

@@ -837,10 +837,11 @@ static int umma_launch_step(const VmbLayout& L, const StepParams& sp, const void
   using namespace um;
   if (L.H != 32 || L.nfreq != 6) { err = "UMMA step kernel: hidden must be 32 and n_freq 6"; return -4; }
   if (sp.S > UMMA_MAX_S) { err = "UMMA step kernel: n_samples > 16"; return -4; }
-  static int n_sm = 0;
+  static int n_sm_dev[64] = {};            // per device (one process may drive several GPUs)
+  int dev = 0;
+  cudaGetDevice(&dev);
+  int& n_sm = n_sm_dev[dev & 63];
   if (n_sm == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
     cudaError_t e = cudaFuncSetAttribute(k_step_umma<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_step_umma<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);

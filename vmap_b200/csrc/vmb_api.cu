@@ -41,10 +41,10 @@ static int fail(vmb_handle* h, int code, const std::string& msg) {
 template <int H, int TP>
 static int launch_fp32(vmb_handle* h, const StepParams& sp, long long n_tiles_x, cudaStream_t st) {
   const size_t smem = step_fp32_smem<H, TP>(h->L);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[64] = {};          // per device (one process may drive several GPUs)
+  if (!attr_set[h->device & 63]) {
     CUDA_TRY(h, cudaFuncSetAttribute(k_step_fp32<H, TP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
+    attr_set[h->device & 63] = true;
   }
   dim3 grid((unsigned)n_tiles_x, (unsigned)sp.B);
   k_step_fp32<H, TP><<<grid, 128, smem, st>>>(sp, h->L);
