@@ -40,7 +40,8 @@ enum {
 enum {
   VMB_IMPL_AUTO = 0,
   VMB_IMPL_FP32 = 1,    /* CUDA-core fp32 kernel, any hidden size (parity anchor)            */
-  VMB_IMPL_UMMA = 2     /* tcgen05/TMEM fp16-operand kernel, hidden = 32 (the fast path)      */
+  VMB_IMPL_UMMA = 2,    /* tcgen05/TMEM fp16-operand fused kernel, hidden = 32 (the fast path) */
+  VMB_IMPL_LAYERWISE = 3 /* tcgen05 GEMM per layer over all points, hidden = 64/128/256 (bg / iMAP) */
 };
 
 /* status word bits (vmb_step_args.status / vmb_adam_args.status, device int[4]) */
@@ -193,6 +194,14 @@ typedef struct vmb_sample_args {
 } vmb_sample_args;
 
 int vmb_sample(vmb_handle* h, const vmb_sample_args* a, void* stream);
+
+/* ---- bring-up / test hook (not part of the reference-facing surface) --------------------------- */
+/* Generic tcgen05 GEMM of the layer-wise wide-model path: D[M][N] = A[M][K1+K2] * B[N][K]^T, fp16 in,
+ * fp32 accumulate.  a_mn/b_mn = 0: operand stored [rows][ld] with K contiguous; 1: stored [K][ld] with
+ * M/N contiguous.  epi 0: out16 = relu(acc*scale + bias); 2: out32 (=|+=) acc*scale; 3: atomicAdd.   */
+int vmb_debug_gemm(int a_mn, int b_mn, int epi, int M, int N, int K1, int K2, const void* a1, long long a1_ld,
+                   const void* a2, long long a2_ld, const void* b, long long b_ld, const float* bias, void* out16,
+                   int ldo, float* out32, int ld32, int accumulate, int ksplit, float scale, void* stream);
 
 #ifdef __cplusplus
 }

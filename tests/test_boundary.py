@@ -49,7 +49,7 @@ def test_bad_arguments_return_error_codes_not_crashes():
     L = _lib.lib()
     assert L.vmb_param_count(0, 6) < 0
     assert L.vmb_param_count(32, 99) < 0
-    assert L.vmb_image_bytes(256, 6) == 0
+    assert L.vmb_image_bytes(48, 6) == 0 and L.vmb_image_bytes(256, 6) == 2 * 256 * (4 * 256 + 240)
     assert L.vmb_step(None, None, None) < 0
     assert L.vmb_adam(None, None, None) < 0
     assert L.vmb_sample(None, None, None) < 0

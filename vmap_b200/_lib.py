@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("VMB_LIB") or os.path.join(_HERE, "libvmap_b200.so")   # VMB_LIB: profiling variants
 CSRC = os.path.join(_HERE, "csrc")
 
-VMB_IMPL = {"auto": 0, "fp32": 1, "umma": 2}
+VMB_IMPL = {"auto": 0, "fp32": 1, "umma": 2, "layerwise": 3}
 VMB_ST_LOSS_EXPLODE = 1
 VMB_ST_NONFINITE = 2
 N_TENSORS = 15
@@ -79,7 +79,7 @@ class SampleArgs(C.Structure):
 EXPORTS = (
     "vmb_version", "vmb_param_count", "vmb_param_stride", "vmb_param_offsets", "vmb_image_bytes",
     "vmb_create", "vmb_destroy", "vmb_last_error", "vmb_step", "vmb_mask_counts", "vmb_adam",
-    "vmb_build_image", "vmb_forward", "vmb_sample",
+    "vmb_build_image", "vmb_forward", "vmb_sample", "vmb_debug_gemm",
 )
 
 _lib = None
@@ -126,6 +126,8 @@ def lib():
         L.vmb_sample.argtypes = [_vp, C.POINTER(SampleArgs), _vp]
         L.vmb_build_image.argtypes = [_vp, C.c_int, _vp, _vp, _vp]
         L.vmb_mask_counts.argtypes = [_vp, C.c_int, C.c_int, _vp, _ll, _vp, _ll, _vp, _vp]
+        L.vmb_debug_gemm.argtypes = [C.c_int] * 7 + [_vp, _ll, _vp, _ll, _vp, _ll, _vp, _vp, C.c_int, _vp, C.c_int,
+                                     C.c_int, C.c_int, C.c_float, _vp]
         _lib = L
         return _lib
 

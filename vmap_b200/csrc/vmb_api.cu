@@ -12,6 +12,8 @@
 #include "k_adam.cuh"
 #include "k_sampler.cuh"
 #include "k_step_umma.cuh"
+#include "k_gemm_umma.cuh"
+#include "k_layerwise.cuh"
 
 struct vmb_handle {
   int device, max_obj, H, nfreq;
@@ -20,7 +22,9 @@ struct vmb_handle {
   int* d_img_index;       // [P] param index -> half index inside the fp16 image (or -1)
   unsigned int* d_ticket; // last-block ticket of the fused AdamW (device step counter mode)
   int img_halves;
-  bool umma_ok;
+  bool umma_ok;           // hidden 32: fused tcgen05 kernel + its pre-swizzled fp16 image
+  bool lw_ok;             // hidden 64/128/256: layer-wise tcgen05 GEMM path + row-major fp16 image
+  lw::Workspace ws;
   std::string err;
 };
 
@@ -92,6 +96,7 @@ int vmb_param_offsets(int hidden, int n_freq, int* offsets, int* sizes) {
 }
 int vmb_image_bytes(int hidden, int n_freq) {
   if (hidden == 32 && n_freq == 6) return umma_image_bytes();
+  if ((hidden == 64 || hidden == 128 || hidden == 256) && n_freq == 6) return (int)(2 * lw::img_halves(hidden));
   return 0;
 }
 
@@ -106,7 +111,7 @@ int vmb_create(vmb_handle** out, int device, int max_obj, int hidden, int n_freq
   vmb_handle* h = new vmb_handle();
   h->device = device; h->max_obj = max_obj; h->H = hidden; h->nfreq = n_freq;
   h->L = vmb_make_layout(hidden, n_freq);
-  h->d_counts = nullptr; h->d_img_index = nullptr; h->d_ticket = nullptr; h->img_halves = 0; h->umma_ok = false;
+  h->d_counts = nullptr; h->d_img_index = nullptr; h->d_ticket = nullptr; h->img_halves = 0; h->umma_ok = false; h->lw_ok = false;
   cudaError_t e = cudaMalloc(&h->d_counts, sizeof(int) * 4 * max_obj);
   if (e == cudaSuccess) e = cudaMalloc(&h->d_ticket, sizeof(unsigned int));
   if (e == cudaSuccess) e = cudaMemset(h->d_ticket, 0, sizeof(unsigned int));
@@ -119,6 +124,14 @@ int vmb_create(vmb_handle** out, int device, int max_obj, int hidden, int n_freq
     if (e == cudaSuccess) e = cudaMemcpy(h->d_img_index, idx.data(), sizeof(int) * h->L.P, cudaMemcpyHostToDevice);
     if (e != cudaSuccess) { cudaFree(h->d_counts); delete h; return fail(nullptr, VMB_E_CUDA, cudaGetErrorString(e)); }
     h->umma_ok = true;
+  } else if ((hidden == 64 || hidden == 128 || hidden == 256) && n_freq == 6) {
+    std::vector<int> idx(h->L.P);
+    lw::fill_image_index(h->L, idx.data());
+    h->img_halves = (int)lw::img_halves(hidden);
+    e = cudaMalloc(&h->d_img_index, sizeof(int) * h->L.P);
+    if (e == cudaSuccess) e = cudaMemcpy(h->d_img_index, idx.data(), sizeof(int) * h->L.P, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { cudaFree(h->d_counts); delete h; return fail(nullptr, VMB_E_CUDA, cudaGetErrorString(e)); }
+    h->lw_ok = true;
   }
   *out = h;
   return VMB_OK;
@@ -130,6 +143,7 @@ void vmb_destroy(vmb_handle* h) {
   if (h->d_counts) cudaFree(h->d_counts);
   if (h->d_img_index) cudaFree(h->d_img_index);
   if (h->d_ticket) cudaFree(h->d_ticket);
+  h->ws.release();
   delete h;
 }
 
@@ -162,7 +176,8 @@ int vmb_step(vmb_handle* h, const vmb_step_args* a, void* stream) {
   }
   int impl = a->impl;
   const bool umma_possible = h->umma_ok && a->image != nullptr && a->n_samples <= UMMA_MAX_S;
-  if (impl == VMB_IMPL_AUTO) impl = umma_possible ? VMB_IMPL_UMMA : VMB_IMPL_FP32;
+  const bool lw_possible = h->lw_ok && a->image != nullptr;
+  if (impl == VMB_IMPL_AUTO) impl = umma_possible ? VMB_IMPL_UMMA : (lw_possible ? VMB_IMPL_LAYERWISE : VMB_IMPL_FP32);
   StepParams sp;
   memset(&sp, 0, sizeof(sp));
   sp.B = a->n_obj; sp.R = a->n_rays; sp.S = a->n_samples;
@@ -184,6 +199,13 @@ int vmb_step(vmb_handle* h, const vmb_step_args* a, void* stream) {
     if (!umma_possible) return fail(h, VMB_E_UNSUPPORTED, "vmb_step: UMMA path needs hidden=32, n_freq=6, an image and S<=16");
     std::string err;
     const int rc = umma_launch_step(h->L, sp, a->image, st, err);
+    if (rc != VMB_OK) return fail(h, rc, err);
+    return VMB_OK;
+  }
+  if (impl == VMB_IMPL_LAYERWISE) {
+    if (!lw_possible) return fail(h, VMB_E_UNSUPPORTED, "vmb_step: layer-wise path needs hidden 64/128/256, n_freq=6 and an image");
+    std::string err;
+    const int rc = lw::launch_step(h->ws, h->L, sp, a->image, st, err);
     if (rc != VMB_OK) return fail(h, rc, err);
     return VMB_OK;
   }
@@ -211,7 +233,7 @@ int vmb_adam(vmb_handle* h, const vmb_adam_args* a, void* stream) {
   if (!h || !a || a->n_obj <= 0 || a->n_obj > h->max_obj || (a->step < 1 && !a->step_counter) || !a->params || !a->grads ||
       !a->exp_avg || !a->exp_avg_sq)
     return fail(h, VMB_E_ARG, "vmb_adam: bad arguments");
-  if (a->image && !h->umma_ok) return fail(h, VMB_E_UNSUPPORTED, "vmb_adam: no fp16 image for this hidden size");
+  if (a->image && !h->umma_ok && !h->lw_ok) return fail(h, VMB_E_UNSUPPORTED, "vmb_adam: no fp16 image for this hidden size");
   AdamParams p;
   memset(&p, 0, sizeof(p));
   p.n = (long long)a->n_obj * h->L.stride; p.stride = h->L.stride; p.P = h->L.P; p.B = a->n_obj;
@@ -241,7 +263,7 @@ int vmb_adam(vmb_handle* h, const vmb_adam_args* a, void* stream) {
 
 int vmb_build_image(vmb_handle* h, int n_obj, const float* params, void* image, void* stream) {
   if (!h || n_obj <= 0 || n_obj > h->max_obj || !params || !image) return fail(h, VMB_E_ARG, "vmb_build_image: bad arguments");
-  if (!h->umma_ok) return fail(h, VMB_E_UNSUPPORTED, "vmb_build_image: no fp16 image for this hidden size");
+  if (!h->umma_ok && !h->lw_ok) return fail(h, VMB_E_UNSUPPORTED, "vmb_build_image: no fp16 image for this hidden size");
   cudaStream_t st = (cudaStream_t)stream;
   CUDA_TRY(h, cudaMemsetAsync(image, 0, (size_t)n_obj * h->img_halves * 2, st));
   const long long n = (long long)n_obj * h->L.stride;
@@ -270,6 +292,33 @@ int vmb_sample(vmb_handle* h, const vmb_sample_args* a, void* stream) {
   p.sem = a->sem; p.mask = a->mask_depth;
   k_sample<<<a->n_obj, 512, 0, (cudaStream_t)stream>>>(p);
   CUDA_TRY(h, cudaGetLastError());
+  return VMB_OK;
+}
+
+// ---- bring-up / test hook for the generic tcgen05 GEMM of the layer-wise (wide model) path --------
+// a_mn / b_mn = 0: operand stored [M or N rows][ld] with K contiguous; 1: stored [K rows][ld] with M or N contiguous.
+// epi 0: out16 = relu(acc*scale + bias) (fp16);  epi 2: out32 (=|+=) acc*scale;  epi 3: atomicAdd(out32, acc*scale)
+int vmb_debug_gemm(int a_mn, int b_mn, int epi, int M, int N, int K1, int K2, const void* a1, long long a1_ld,
+                   const void* a2, long long a2_ld, const void* b, long long b_ld, const float* bias, void* out16, int ldo,
+                   float* out32, int ld32, int accumulate, int ksplit, float scale, void* stream) {
+  using namespace lw;
+  const int K = K1 + K2;
+  Operand A1{a1, a_mn ? K1 : M, a_mn ? M : K1, a1_ld};
+  Operand A2{a2, a_mn ? K2 : M, a_mn ? M : K2, a2_ld};
+  Operand B{b, b_mn ? K : N, b_mn ? N : K, b_ld};
+  GemmArgs g;
+  memset(&g, 0, sizeof(g));
+  g.M = M; g.N = N; g.K1 = K1; g.K2 = K2; g.ksplit = ksplit; g.bias = bias; g.out16 = (__half*)out16; g.ldo = ldo;
+  g.out32 = out32; g.ld32 = ld32; g.accumulate = accumulate; g.gdst = out32; g.ldgd = ld32; g.ldgn = 1; g.n_lo = 0; g.n_valid = N; g.ones_col = -1;
+  g.scale = scale;
+  const int mt = (M + BM - 1) / BM, nt = (N + BN - 1) / BN, z = ksplit > 0 ? (K + ksplit - 1) / ksplit : 1;
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e = cudaErrorInvalidValue;
+  if (a_mn == 0 && b_mn == 0 && epi == 0) e = launch_gemm<0, 0, EPI_RELU_F16>(A1, A2, B, g, mt, nt, z, st);
+  else if (a_mn == 0 && b_mn == 0 && epi == 2) e = launch_gemm<0, 0, EPI_F32>(A1, A2, B, g, mt, nt, z, st);
+  else if (a_mn == 0 && b_mn == 1 && epi == 2) e = launch_gemm<0, 1, EPI_F32>(A1, A2, B, g, mt, nt, z, st);
+  else if (a_mn == 1 && b_mn == 1 && epi == 3) e = launch_gemm<1, 1, EPI_ATOMIC>(A1, A2, B, g, mt, nt, z, st);
+  if (e != cudaSuccess) return fail(nullptr, VMB_E_CUDA, std::string("vmb_debug_gemm: ") + cudaGetErrorString(e));
   return VMB_OK;
 }
 
