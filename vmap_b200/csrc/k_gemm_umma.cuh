@@ -7,19 +7,20 @@
 // * 128 x 128 output tile per CTA, K in chunks of 64, 3-stage TMA -> mbarrier -> tcgen05.mma pipeline:
 //   warp 4 = TMA producer (one elected lane), warp 5 = MMA issuer, warps 0..3 = epilogue
 //   (TMEM -> registers -> global).  96 KB of shared memory and 128 TMEM columns: two CTAs per SM.
-// * Operands use the SWIZZLE_NONE core-matrix layout verified by tools/umma_probe.cu.  A 3-D tensor
-//   map (8 elements, rows, groups-of-8) makes ONE TMA box land a whole operand stage in exactly that
-//   layout, for both majors:
-//     K-major  operand, global [rows][ld]  (K contiguous):  dims (8, rows, K/8),  box (8, 128, 8)
-//        -> smem (k/8)*2048 + r*16 + (k%8)*2        LBO 2048, SBO 128, k-step +4096
-//     MN-major operand, global [K][ld]     (MN contiguous): dims (8, K, MN/8),    box (8, 64, 16)
-//        -> smem (m/8)*1024 + k*16 + (m%8)*2        LBO 128,  SBO 1024, k-step +256
+// * Operand stages use the 128-byte-swizzle canonical layouts, written by TMA (CU_TENSOR_MAP_SWIZZLE_128B,
+//   128-byte inner box so the TMA engine moves full lines; a first version with 16-byte inner boxes into the
+//   SWIZZLE_NONE layout was TMA-bound at ~150 TFLOP/s):
+//     K-major  operand, global [rows][ld]  (K contiguous):  2-D box (64 k, 128 rows)  -> [128 rows][128 B]
+//        descriptor SWIZZLE_128B, SBO 1024 (8 rows), k-step +32 B inside the swizzle atom
+//     MN-major operand, global [K][ld]     (MN contiguous): two 2-D boxes (64 mn, 64 k) -> two [64 k][128 B] panels
+//        descriptor SWIZZLE_128B, LBO 8192 (next 64-wide panel), SBO 1024 (8 k-rows), k-step +2048 B
 //   Out-of-range rows / columns are zero-filled by the TMA engine, so ragged edges need no branches.
 // * A may come from two sources concatenated along K (e.g. [fc2 | emb1] for cat_layer).
 #pragma once
 #include "common.cuh"
 #include "umma_ptx.cuh"
 #include <cuda.h>
+#include <algorithm>
 
 namespace lw {
 
@@ -35,7 +36,8 @@ struct GemmArgs {
   int M, N;                 // valid output extent
   int K1, K2;               // K taken from A source 1 / source 2 (multiples of 16; K2 may be 0)
   int b_k0;                 // K offset into B for this launch's first chunk (used with split-K on points)
-  int ksplit;               // K elements per blockIdx.z slice (0 = no split)
+  int ksplit;               // K elements per z slice (0 = no split)
+  int mt, nt, zt;           // tile counts (filled by launch_gemm)
   // epilogue
   const float* bias;        // [N] (EPI_RELU_F16)
   __half* out16; int ldo;   // fp16 output
@@ -47,87 +49,115 @@ struct GemmArgs {
   float scale;              // multiplies the accumulator (loss-scale removal)
 };
 
-__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
   asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-      ::"r"(ptx::smem_u32(dst)), "l"(map), "r"(ptx::smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(ptx::smem_u32(dst)), "l"(map), "r"(ptx::smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
+}
+// SWIZZLE_128B shared-memory descriptor (layout type 2)
+__device__ __forceinline__ uint64_t desc_sw128(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return ptx::smem_desc(saddr, lbo_bytes, sbo_bytes) | ((uint64_t)2 << 61);
 }
 
 template <int A_MN, int B_MN, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 2)
 k_gemm_umma(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUtensorMap mapA2,
             const __grid_constant__ CUtensorMap mapB, GemmArgs g) {
+  // Persistent: each CTA walks tiles  t = blockIdx.x, blockIdx.x + gridDim.x, ...  of the (z, m, n) tile space
+  // (n fastest, so the N-tiles of one row block run back to back and share A in L2).  Two TMEM accumulators
+  // (2 x 128 columns) let the MMAs of tile i+1 overlap the epilogue of tile i.
   extern __shared__ __align__(1024) unsigned char smem[];
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + NSTAGE * STAGE_BYTES);
   uint64_t* empty = full + NSTAGE;
-  uint64_t* done = empty + NSTAGE;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
+  uint64_t* tfull = empty + NSTAGE;          // [2] accumulator ready for the epilogue
+  uint64_t* tempty = tfull + 2;              // [2] accumulator drained by the epilogue
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
   const int tid = threadIdx.x, warp = tid >> 5;
-  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
-  // K range of this CTA (split-K along the reduction for the weight-gradient GEMMs)
-  int k_begin = 0, k_end = g.K1 + g.K2;
-  if (g.ksplit > 0) { k_begin = blockIdx.z * g.ksplit; k_end = min(k_end, k_begin + g.ksplit); }
-  const int n_chunks = (k_end - k_begin + BK - 1) / BK;
+  const int n_tiles_total = g.mt * g.nt * g.zt;
+  const int k_total = g.K1 + g.K2;
 
   if (tid == 0) {
     for (int s = 0; s < NSTAGE; ++s) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], 1); }
-    ptx::mbar_init(done, 1);
+    for (int s = 0; s < 2; ++s) { ptx::mbar_init(&tfull[s], 1); ptx::mbar_init(&tempty[s], 128); }
     ptx::mbar_init_fence();
   }
-  if (warp == 5) { ptx::tmem_alloc(tmem_slot, 128); ptx::tmem_relinquish(); }
+  if (warp == 5) { ptx::tmem_alloc(tmem_slot, 256); ptx::tmem_relinquish(); }
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tm = *tmem_slot;
 
+#define TILE_COORDS(T)                                                              \
+  const int tz = (T) / (g.mt * g.nt), trem = (T) - tz * (g.mt * g.nt);              \
+  const int m0 = (trem / g.nt) * BM, n0 = (trem % g.nt) * BN;                       \
+  const int k_begin = g.ksplit > 0 ? tz * g.ksplit : 0;                             \
+  const int k_end = g.ksplit > 0 ? min(k_total, k_begin + g.ksplit) : k_total;      \
+  const int n_chunks = (k_end - k_begin + BK - 1) / BK;
+
   if (warp == 4) {
     // ===================== TMA producer =====================
     if (ptx::elect_one()) {
-      for (int c = 0; c < n_chunks; ++c) {
-        const int s = c % NSTAGE;
-        if (c >= NSTAGE) ptx::mbar_wait(&empty[s], ((c / NSTAGE) - 1) & 1);
-        unsigned char* sa = smem + s * STAGE_BYTES;
-        unsigned char* sb = sa + BM * BK * 2;
-        ptx::mbar_arrive_expect_tx(&full[s], STAGE_BYTES);
-        const int k = k_begin + c * BK;                     // global K position of this chunk
-        // A: source 1 covers [0, K1), source 2 covers [K1, K1+K2); chunks never straddle (K1 % 64 == 0 or K2 == 0)
-        const bool second = (g.K2 > 0) && (k >= g.K1);
-        const CUtensorMap* ma = second ? &mapA2 : &mapA1;
-        const int ka = second ? k - g.K1 : k;
-        if (A_MN) tma_load_3d(sa, ma, &full[s], 0, ka, m0 / 8);           // dims (8, K, M/8)
-        else      tma_load_3d(sa, ma, &full[s], 0, m0, ka / 8);           // dims (8, M, K/8)
-        const int kb = g.b_k0 + k;
-        if (B_MN) tma_load_3d(sb, &mapB, &full[s], 0, kb, n0 / 8);
-        else      tma_load_3d(sb, &mapB, &full[s], 0, n0, kb / 8);
+      uint32_t cc = 0;                        // running chunk counter across tiles
+      for (int t = blockIdx.x; t < n_tiles_total; t += gridDim.x) {
+        TILE_COORDS(t)
+        for (int c = 0; c < n_chunks; ++c, ++cc) {
+          const int s = cc % NSTAGE;
+          if (cc >= NSTAGE) ptx::mbar_wait(&empty[s], ((cc / NSTAGE) - 1) & 1);
+          unsigned char* sa = smem + s * STAGE_BYTES;
+          unsigned char* sb = sa + BM * BK * 2;
+          ptx::mbar_arrive_expect_tx(&full[s], STAGE_BYTES);
+          const int k = k_begin + c * BK;                     // global K position of this chunk
+          // A: source 1 covers [0, K1), source 2 covers [K1, K1+K2); chunks never straddle (K1 % 64 == 0 or K2 == 0)
+          const bool second = (g.K2 > 0) && (k >= g.K1);
+          const CUtensorMap* ma = second ? &mapA2 : &mapA1;
+          const int ka = second ? k - g.K1 : k;
+          if (A_MN) { tma_load_2d(sa, ma, &full[s], m0, ka); tma_load_2d(sa + 8192, ma, &full[s], m0 + 64, ka); }   // dims (M, K)
+          else      tma_load_2d(sa, ma, &full[s], ka, m0);                                                          // dims (K, M)
+          const int kb = g.b_k0 + k;
+          if (B_MN) { tma_load_2d(sb, &mapB, &full[s], n0, kb); tma_load_2d(sb + 8192, &mapB, &full[s], n0 + 64, kb); }
+          else      tma_load_2d(sb, &mapB, &full[s], kb, n0);
+        }
       }
     }
   } else if (warp == 5) {
     // ===================== MMA issuer =====================
     if (ptx::elect_one()) {
       constexpr uint32_t idesc = ptx::idesc_f16(BM, BN, A_MN, B_MN);
-      for (int c = 0; c < n_chunks; ++c) {
-        const int s = c % NSTAGE;
-        ptx::mbar_wait(&full[s], (c / NSTAGE) & 1);
-        ptx::tc_fence_after();
-        const uint32_t sa = ptx::smem_u32(smem + s * STAGE_BYTES), sb = sa + BM * BK * 2;
-        const int klen = min(BK, k_end - (k_begin + c * BK));
+      uint32_t cc = 0, it = 0;
+      for (int t = blockIdx.x; t < n_tiles_total; t += gridDim.x, ++it) {
+        TILE_COORDS(t)
+        (void)m0; (void)n0;
+        const uint32_t acc = it & 1u;
+        if (it >= 2) { ptx::mbar_wait(&tempty[acc], ((it >> 1) - 1) & 1); ptx::tc_fence_after(); }
+        for (int c = 0; c < n_chunks; ++c, ++cc) {
+          const int s = cc % NSTAGE;
+          ptx::mbar_wait(&full[s], (cc / NSTAGE) & 1);
+          ptx::tc_fence_after();
+          const uint32_t sa = ptx::smem_u32(smem + s * STAGE_BYTES), sb = sa + BM * BK * 2;
+          const int klen = min(BK, k_end - (k_begin + c * BK));
 #pragma unroll 1
-        for (int ks = 0; ks * 16 < klen; ++ks) {
-          const uint64_t ad = A_MN ? ptx::smem_desc(sa + ks * 256, 128, 1024) : ptx::smem_desc(sa + ks * 4096, 2048, 128);
-          const uint64_t bd = B_MN ? ptx::smem_desc(sb + ks * 256, 128, 1024) : ptx::smem_desc(sb + ks * 4096, 2048, 128);
-          ptx::umma_f16(tm, ad, bd, idesc, (c > 0 || ks > 0) ? 1u : 0u);
+          for (int ks = 0; ks * 16 < klen; ++ks) {
+            const uint64_t ad = A_MN ? desc_sw128(sa + ks * 2048, 8192, 1024) : desc_sw128(sa + ks * 32, 16, 1024);
+            const uint64_t bd = B_MN ? desc_sw128(sb + ks * 2048, 8192, 1024) : desc_sw128(sb + ks * 32, 16, 1024);
+            ptx::umma_f16(tm + acc * BN, ad, bd, idesc, (c > 0 || ks > 0) ? 1u : 0u);
+          }
+          ptx::umma_commit(&empty[s]);
         }
-        ptx::umma_commit(&empty[s]);
+        ptx::umma_commit(&tfull[acc]);
       }
-      ptx::umma_commit(done);
     }
   } else {
     // ===================== epilogue: TMEM lane = output row =====================
-    ptx::mbar_wait(done, 0);
+    uint32_t it = 0;
+    for (int t = blockIdx.x; t < n_tiles_total; t += gridDim.x, ++it) {
+    TILE_COORDS(t)
+    (void)n_chunks; (void)k_end;
+    const uint32_t acc = it & 1u;
+    ptx::mbar_wait(&tfull[acc], (it >> 1) & 1);
     ptx::tc_fence_after();
     const int m = m0 + tid;
-    const uint32_t taddr = tm + ((uint32_t)(warp * 32) << 16);
+    const uint32_t taddr = tm + ((uint32_t)(warp * 32) << 16) + acc * BN;
 #pragma unroll 1
     for (int c32 = 0; c32 < BN; c32 += 32) {
       if (n0 + c32 >= g.N) break;                           // warp-uniform
@@ -187,10 +217,14 @@ k_gemm_umma(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ C
         }
       }
     }
+    ptx::tc_fence_before();
+    ptx::mbar_arrive(&tempty[acc]);            // this thread has drained its lanes of the accumulator
+    }
   }
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == 5) ptx::tmem_dealloc(tm, 128);
+  if (warp == 5) ptx::tmem_dealloc(tm, 256);
+#undef TILE_COORDS
 }
 
 // ---- host: tensor maps ----------------------------------------------------------------------
@@ -211,17 +245,17 @@ static PFN_encodeTiled get_encode() {
 }
 
 // fp16 matrix with `rows` rows of `cols` contiguous elements, row pitch `ld` elements.
-//   mn_major = 0: the matrix is [rows = M or N][cols = K]   (K contiguous)   -> box (8, 128, 8)
-//   mn_major = 1: the matrix is [rows = K][cols = M or N]   (MN contiguous)  -> box (8, 64, 16)
+//   mn_major = 0: the matrix is [rows = M or N][cols = K]   (K contiguous)   -> box (64 k, 128 rows)
+//   mn_major = 1: the matrix is [rows = K][cols = M or N]   (MN contiguous)  -> box (64 mn, 64 k), two per stage
 static bool make_operand_map(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld, int mn_major) {
   PFN_encodeTiled enc = get_encode();
   if (!enc) return false;
-  cuuint64_t dims[3] = {8, (cuuint64_t)rows, (cuuint64_t)(cols / 8)};
-  cuuint64_t strides[2] = {(cuuint64_t)ld * 2, 16};
-  cuuint32_t box[3] = {8, (cuuint32_t)(mn_major ? BK : BM), (cuuint32_t)(mn_major ? BM / 8 : BK / 8)};
-  cuuint32_t estr[3] = {1, 1, 1};
-  return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
-             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {64, (cuuint32_t)(mn_major ? BK : BM)};
+  cuuint32_t estr[2] = {1, 1};
+  return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
@@ -243,7 +277,12 @@ static cudaError_t launch_gemm(const Operand& a1, const Operand& a2, const Opera
   if (a2.base) { if (!make_operand_map(&mA2, a2.base, a2.rows, a2.cols, a2.ld, A_MN)) return cudaErrorInvalidValue; }
   else mA2 = mA1;
   if (!make_operand_map(&mB, b.base, b.rows, b.cols, b.ld, B_MN)) return cudaErrorInvalidValue;
-  k_gemm_umma<A_MN, B_MN, EPI><<<dim3(m_tiles, n_tiles, z), GEMM_THREADS, GEMM_SMEM, st>>>(mA1, mA2, mB, g);
+  static int n_sm[64] = {};
+  if (!n_sm[dev & 63]) cudaDeviceGetAttribute(&n_sm[dev & 63], cudaDevAttrMultiProcessorCount, dev);
+  g.mt = m_tiles; g.nt = n_tiles; g.zt = z;
+  const long long total = (long long)m_tiles * n_tiles * z;
+  const int grid = (int)std::min<long long>(total, 2LL * n_sm[dev & 63]);
+  k_gemm_umma<A_MN, B_MN, EPI><<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(mA1, mA2, mB, g);
   return cudaGetLastError();
 }
 
