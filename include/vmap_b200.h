@@ -191,9 +191,48 @@ typedef struct vmb_sample_args {
   unsigned char* gt_rgb_u8;  /* optional [B][N][3] raw bytes as the reference returns them */
   unsigned char* sem;        /* [B][N]                                                     */
   unsigned char* mask_depth; /* [B][N]                                                     */
+  /* Shared keyframe store (optional).  When store_rgbx != NULL the per-object pointer
+   * tables rgbs/depths/t_wc/bbox above are ignored: every frame is stored once (instead of once per
+   * object, vmap.py:137-176) and the pixel state the reference keeps in rgbs_batch[...,3] is derived
+   * from the instance image as train.py:126-128 builds it (id == obj -> 1, id == -1 -> 2, else 0).  */
+  const unsigned char* store_rgbx;  /* [slots][W][H][4] u8: r,g,b,unused                           */
+  const float* store_depth;         /* [slots][W][H]                                               */
+  const int* store_inst;            /* [slots][W][H] instance id per pixel (-1 = unknown)          */
+  const float* store_t_wc;          /* [slots][4][4]                                               */
+  const int* kf_slot;               /* [B][kf_stride] store slot of each object's keyframe         */
+  const float* kf_bbox;             /* [B][kf_stride][4] u_lo,u_hi,v_lo,v_hi                       */
+  const int* obj_id;                /* [B] instance id of each object                              */
+  int kf_stride;
 } vmb_sample_args;
 
 int vmb_sample(vmb_handle* h, const vmb_sample_args* a, void* stream);
+
+/* ---- K4: frame ingest ----------------------------------------------------------------------------
+ * One GPU pass over the instance image of a new frame.  Replaces the per-frame numpy loop of
+ * dataset.py:101-131 (np.unique, a boolean mask per instance, utils.get_bbox2d_batch utils.py:75-84,
+ * utils.enlarge_bbox utils.py:36-57, the "inst[obj_ == 0] = 0" relabel) and, with the shared keyframe
+ * store, the per-object state-mask build and full-frame copies of train.py:121-141.
+ * Images are stored [W][H] as the reference keeps them (dataset.py:87-91 transposes).                */
+typedef struct vmb_ingest_args {
+  int width, height;
+  const int* inst;               /* [W][H] int32 instance id per pixel; ids outside [0,max_id) are not tabulated */
+  const int* cls;                /* optional [W][H] int32 semantic class per pixel                               */
+  int max_id;
+  float bbox_scale;              /* dataset bbox_scale (enlarge_bbox's scale)                                    */
+  int min_extent;                /* instances with an extent <= this are dropped (dataset.py:119 uses 10)        */
+  const unsigned char* bg_class; /* optional [n_class]: 1 = background class (dataset.py:106)                    */
+  int n_class;
+  int* stats;                    /* out [max_id][8]: count, u_min, u_max+1, v_min, v_max+1, cls_min, cls_max, keep */
+  float* bbox;                   /* out [max_id][4]: enlarged u_lo,u_hi,v_lo,v_hi (meaningful where keep)        */
+  /* optional fused write of the frame into a slot of the shared keyframe store (all or none of dst_*)           */
+  const unsigned char* rgb;      /* [W][H][3] u8                                                                 */
+  const float* depth;            /* [W][H]                                                                       */
+  unsigned char* dst_rgbx;       /* [W][H][4]                                                                    */
+  float* dst_depth;              /* [W][H]                                                                       */
+  int* dst_inst;                 /* [W][H]: dropped instances relabelled 0 (dataset.py:128), -1 kept             */
+} vmb_ingest_args;
+
+int vmb_ingest_frame(vmb_handle* h, const vmb_ingest_args* a, void* stream);
 
 /* ---- bring-up / test hook (not part of the reference-facing surface) --------------------------- */
 /* Generic tcgen05 GEMM of the layer-wise wide-model path: D[M][N] = A[M][K1+K2] * B[N][K]^T, fp16 in,

@@ -167,8 +167,72 @@ def reference_config_case():
     print("config_room0", sorted(out["vMAP"]["attrs"])[:5], "...")
 
 
+def reference_ingest_case(name, W, H, n_inst, seed, depth_scale=1000.0):
+    """Run the reference's OWN data loader (dataset.Replica.__getitem__, dataset.py:80-141) on a synthetic
+    Replica-format directory written under a scratch folder of this repo: the golden holds the instance /
+    class images it read and the bbox_dict / relabelled instance image it returned."""
+    import shutil
+    import tempfile
+    import types
+
+    import cv2
+    import numpy as np
+
+    from oracle import ingest_oracle as io
+
+    dataset = _refload.load("dataset")
+    inst, cls = io.synthetic_instance_frame(W, H, n_inst, seed)
+    root = tempfile.mkdtemp(prefix="_ds_", dir=os.path.dirname(os.path.abspath(__file__)))
+    try:
+        for d in ("rgb", "depth", "semantic_instance", "semantic_class"):
+            os.makedirs(os.path.join(root, d))
+        rng = np.random.default_rng(seed)
+        # files are stored [H][W]; the loader transposes to [W][H] (dataset.py:87-91)
+        cv2.imwrite(os.path.join(root, "rgb", "rgb_0.png"), rng.integers(0, 255, (H, W, 3), dtype=np.uint8))
+        cv2.imwrite(os.path.join(root, "depth", "depth_0.png"), rng.integers(500, 4000, (H, W)).astype(np.uint16))
+        cv2.imwrite(os.path.join(root, "semantic_instance", "semantic_instance_0.png"), inst.T.astype(np.uint16))
+        cv2.imwrite(os.path.join(root, "semantic_class", "semantic_class_0.png"), cls.T.astype(np.uint16))
+        np.savetxt(os.path.join(root, "traj_w_c.txt"), np.eye(4).reshape(1, 16), delimiter=" ")
+        cfg = types.SimpleNamespace(imap_mode=False, dataset_dir=root, depth_scale=depth_scale, max_depth=8.0)
+        ds = dataset.Replica(cfg)
+        sample = ds[0]
+        bbox_dict = {int(k): np.asarray(v).astype(np.int64) for k, v in sample["bbox_dict"].items()}
+        obj = np.asarray(sample["obj"]).astype(np.int32)
+        ids = np.array(sorted(bbox_dict), dtype=np.int64)
+        np.savez_compressed(os.path.join(OUT, name + ".npz"), inst=inst.astype(np.int16), cls=cls.astype(np.int16),
+                            background_cls=np.array(ds.background_cls_list, dtype=np.int64),
+                            bbox_scale=np.float64(ds.bbox_scale), ids=ids,
+                            bboxes=np.stack([bbox_dict[int(i)] for i in ids]), obj=obj.astype(np.int16))
+        print(name, "instances in frame", len(np.unique(inst)), "kept", len(ids))
+    finally:
+        shutil.rmtree(root, ignore_errors=True)
+
+
+def reference_enlarge_table():
+    """utils.enlarge_bbox on every extent 1..1300 at the scales the repo ships / plausible ones: pins the
+    float32 truncation of int(0.5*scale*extent) when the extent is a torch int64 scalar (dataset.py:121)."""
+    import numpy as np
+    import torch
+    utils = _refload.load("utils")
+    scales = [0.2, 0.1, 0.5, 1.0, 0.3, 1.5]
+    ext = np.arange(1, 1301)
+    margins = np.zeros((len(scales), ext.size), dtype=np.int64)
+    for si, sc in enumerate(scales):
+        for ei, e in enumerate(ext):
+            # big canvas so clipping does not hide the margin; both axes share the extent
+            r = utils.enlarge_bbox([torch.tensor(2000), torch.tensor(2000), torch.tensor(2000 + int(e)),
+                                    torch.tensor(2000 + int(e))], scale=sc, w=10000, h=10000)
+            margins[si, ei] = 0 if r is None else 2000 - r[0]
+    np.savez_compressed(os.path.join(OUT, "ingest_enlarge_table.npz"), scales=np.array(scales), extents=ext,
+                        margins=margins)
+    print("ingest_enlarge_table", margins[:, [9, 10, 99, 1199]].tolist())
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    reference_ingest_case("ingest_small", W=160, H=120, n_inst=14, seed=21)
+    reference_ingest_case("ingest_replica_size", W=1200, H=680, n_inst=40, seed=22)
+    reference_enlarge_table()
     reference_config_case()
     # vMAP object ensemble (room0_vMAP.json: H=32, scale 2, 1+9 samples), 3 AdamW steps
     reference_step_case("step_vmap_h32", n_obj=3, hidden=32, n_rays=24, n_samples=10, scale=2.0,

@@ -10,19 +10,22 @@ from tests._util import make_ensemble, rel_l2, to_dev
 pytestmark = pytest.mark.gpu
 
 
-def test_cfg0_imap_single_mlp_h256_100rays():
-    """configs[0]: iMAP single-scene MLP, 1 object, 100 rays x 10 samples, hidden 256 (CPU-runnable)."""
+@pytest.mark.parametrize("impl", ["fp32", "auto"])
+def test_cfg0_imap_single_mlp_h256_100rays(impl):
+    """configs[0]: iMAP single-scene MLP, 1 object, 100 rays x 10 samples, hidden 256 (CPU-runnable).
+    "fp32" is the CUDA-core parity anchor; "auto" resolves to the layer-wise tensor-core path (fp16 operands)."""
     params = vo.init_params(1, 256, seed=0)
     batch = vo.synthetic_batch(1, 100, 10, seed=1, n_cam2surf=5)
     orc = vo.OracleEnsemble(params, 5.0)
-    ens = make_ensemble(params, 5.0, 256, impl="auto")           # falls to the fp32 kernel (H != 32)
+    ens = make_ensemble(params, 5.0, 256, impl=impl)
     db = to_dev(batch)
+    tol_loss, tol_par = (2e-4, 1e-4) if impl == "fp32" else (3e-3, 2e-2)
     for _ in range(3):
         l_ref = float(orc.step(batch))
         l = float(ens.step(db))
-        assert abs(l - l_ref) < 2e-4 * abs(l_ref)
+        assert abs(l - l_ref) < tol_loss * abs(l_ref)
     for k in vo.ALL_KEYS:      # Adam normalises near-zero gradients, so atomics-order noise shows up at ~1e-5
-        assert rel_l2(ens.view(k), orc.params[k]) < 1e-4, k
+        assert rel_l2(ens.view(k), orc.params[k]) < tol_par, k
 
 
 @pytest.mark.parametrize("n_obj", [50, 160])

@@ -73,13 +73,24 @@ class SampleArgs(C.Structure):
         ("inj_kf", _vp), ("inj_u_w", _vp), ("inj_u_h", _vp), ("inj_u_z", _vp), ("inj_nrm", _vp),
         ("pcs", _vp), ("z_vals", _vp), ("gt_depth", _vp), ("gt_colour", _vp), ("gt_rgb_u8", _vp),
         ("sem", _vp), ("mask_depth", _vp),
+        ("store_rgbx", _vp), ("store_depth", _vp), ("store_inst", _vp), ("store_t_wc", _vp),
+        ("kf_slot", _vp), ("kf_bbox", _vp), ("obj_id", _vp), ("kf_stride", C.c_int),
+    ]
+
+
+class IngestArgs(C.Structure):
+    _fields_ = [
+        ("width", C.c_int), ("height", C.c_int), ("inst", _vp), ("cls", _vp), ("max_id", C.c_int),
+        ("bbox_scale", C.c_float), ("min_extent", C.c_int), ("bg_class", _vp), ("n_class", C.c_int),
+        ("stats", _vp), ("bbox", _vp), ("rgb", _vp), ("depth", _vp),
+        ("dst_rgbx", _vp), ("dst_depth", _vp), ("dst_inst", _vp),
     ]
 
 
 EXPORTS = (
     "vmb_version", "vmb_param_count", "vmb_param_stride", "vmb_param_offsets", "vmb_image_bytes",
     "vmb_create", "vmb_destroy", "vmb_last_error", "vmb_step", "vmb_mask_counts", "vmb_adam",
-    "vmb_build_image", "vmb_forward", "vmb_sample", "vmb_debug_gemm",
+    "vmb_build_image", "vmb_forward", "vmb_sample", "vmb_ingest_frame", "vmb_debug_gemm",
 )
 
 _lib = None
@@ -124,6 +135,7 @@ def lib():
         L.vmb_adam.argtypes = [_vp, C.POINTER(AdamArgs), _vp]
         L.vmb_forward.argtypes = [_vp, C.POINTER(ForwardArgs), _vp]
         L.vmb_sample.argtypes = [_vp, C.POINTER(SampleArgs), _vp]
+        L.vmb_ingest_frame.argtypes = [_vp, C.POINTER(IngestArgs), _vp]
         L.vmb_build_image.argtypes = [_vp, C.c_int, _vp, _vp, _vp]
         L.vmb_mask_counts.argtypes = [_vp, C.c_int, C.c_int, _vp, _ll, _vp, _ll, _vp, _vp]
         L.vmb_debug_gemm.argtypes = [C.c_int] * 7 + [_vp, _ll, _vp, _ll, _vp, _ll, _vp, _vp, C.c_int, _vp, C.c_int,

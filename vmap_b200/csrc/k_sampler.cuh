@@ -27,7 +27,15 @@ struct SampleParams {
   const long long* inj_kf; const float* inj_u_w; const float* inj_u_h; const float* inj_u_z; const float* inj_nrm;
   float* pcs; float* z; float* gt_depth; float* gt_colour; unsigned char* rgb_u8;
   unsigned char* sem; unsigned char* mask;
+  // shared keyframe store (optional): frames are stored once, objects hold (slot, bbox) tables and the pixel
+  // state is derived from the instance image (train.py:126-128: this object -> 1, id -1 -> 2, else 0)
+  const uchar4* st_rgbx; const float* st_depth; const int* st_inst; const float* st_twc;
+  const int* kf_slot; const float* bbox_flat; const int* obj_id; int kf_stride;
 };
+
+__device__ __forceinline__ const float* sample_bbox(const SampleParams& a, int b, int kf) {
+  return a.st_rgbx ? a.bbox_flat + ((size_t)b * a.kf_stride + kf) * 4 : a.bbox[b] + kf * 4;
+}
 
 __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
                                               uint32_t k0, uint32_t k1, uint32_t (&out)[4]) {
@@ -68,7 +76,7 @@ __device__ __forceinline__ RayPick pick_pixel(const SampleParams& a, int b, int 
     philox4x32_10((uint32_t)i, 1u, (uint32_t)b, (uint32_t)a.offset, k0, k1, o);
     uw = u01(o[0]); uh = u01(o[1]);
   }
-  const float* bb = a.bbox[b] + r.kf * 4;                         // vmap.py:346-351
+  const float* bb = sample_bbox(a, b, r.kf);                       // vmap.py:346-351
   r.iw = (int)__fadd_rn(__fmul_rn(uw, __fsub_rn(bb[1], bb[0])), bb[0]);
   r.ih = (int)__fadd_rn(__fmul_rn(uh, __fsub_rn(bb[3], bb[2])), bb[2]);
   r.iw = min(max(r.iw, 0), a.W - 1);
@@ -95,9 +103,19 @@ __global__ void __launch_bounds__(512) k_sample(SampleParams a) {
   float mx = -3.0e38f;
   for (int i = threadIdx.x; i < N; i += blockDim.x) {
     const RayPick r = pick_pixel(a, b, i);
-    const size_t pi = (size_t)r.kf * pix_per_kf + (size_t)r.iw * a.Hh + r.ih;
-    const uchar4 px = reinterpret_cast<const uchar4*>(a.rgbs[b])[pi];
-    const float d = a.depths[b][pi];
+    uchar4 px;
+    float d;
+    if (a.st_rgbx) {
+      const size_t pi = (size_t)a.kf_slot[(size_t)b * a.kf_stride + r.kf] * pix_per_kf + (size_t)r.iw * a.Hh + r.ih;
+      px = a.st_rgbx[pi];
+      d = a.st_depth[pi];
+      const int id = a.st_inst[pi];
+      px.w = id == a.obj_id[b] ? 1 : (id == -1 ? 2 : 0);
+    } else {
+      const size_t pi = (size_t)r.kf * pix_per_kf + (size_t)r.iw * a.Hh + r.ih;
+      px = reinterpret_cast<const uchar4*>(a.rgbs[b])[pi];
+      d = a.depths[b][pi];
+    }
     const size_t o = (size_t)b * N + i;
     a.gt_depth[o] = d;
     a.gt_colour[o * 3 + 0] = (float)px.x / 255.f;                 // train.py:257
@@ -166,7 +184,8 @@ __global__ void __launch_bounds__(512) k_sample(SampleParams a) {
     }
 
     const float* dc = a.rays_dir + ((size_t)r.iw * a.Hh + r.ih) * 3;   // vmap.py:357
-    const float* T = a.t_wc[b] + r.kf * 16;                            // vmap.py:360
+    const float* T = a.st_rgbx ? a.st_twc + (size_t)a.kf_slot[(size_t)b * a.kf_stride + r.kf] * 16
+                               : a.t_wc[b] + r.kf * 16;                // vmap.py:360
     const float dw0 = fmaf(T[2], dc[2], fmaf(T[1], dc[1], T[0] * dc[0]));      // vmap.py:37
     const float dw1 = fmaf(T[6], dc[2], fmaf(T[5], dc[1], T[4] * dc[0]));
     const float dw2 = fmaf(T[10], dc[2], fmaf(T[9], dc[1], T[8] * dc[0]));

@@ -11,12 +11,14 @@
 #include "k_step_fp32.cuh"
 #include "k_adam.cuh"
 #include "k_sampler.cuh"
+#include "k_ingest.cuh"
 #include "k_step_umma.cuh"
 #include "k_gemm_umma.cuh"
 #include "k_layerwise.cuh"
 
 struct vmb_handle {
   int device, max_obj, H, nfreq;
+  int n_sm;
   VmbLayout L;
   int* d_counts;          // [max_obj][4]
   int* d_img_index;       // [P] param index -> half index inside the fp16 image (or -1)
@@ -110,6 +112,8 @@ int vmb_create(vmb_handle** out, int device, int max_obj, int hidden, int n_freq
   CUDA_TRY(nullptr, cudaSetDevice(device));
   vmb_handle* h = new vmb_handle();
   h->device = device; h->max_obj = max_obj; h->H = hidden; h->nfreq = n_freq;
+  h->n_sm = 148;
+  cudaDeviceGetAttribute(&h->n_sm, cudaDevAttrMultiProcessorCount, device);
   h->L = vmb_make_layout(hidden, n_freq);
   h->d_counts = nullptr; h->d_img_index = nullptr; h->d_ticket = nullptr; h->img_halves = 0; h->umma_ok = false; h->lw_ok = false;
   cudaError_t e = cudaMalloc(&h->d_counts, sizeof(int) * 4 * max_obj);
@@ -278,7 +282,13 @@ int vmb_sample(vmb_handle* h, const vmb_sample_args* a, void* stream) {
     return fail(h, VMB_E_ARG, "vmb_sample: bad arguments");
   if (a->n_bins_cam2surface < 1 || a->n_bins < 1 || a->n_bins_cam2surface + a->n_bins > 32)
     return fail(h, VMB_E_ARG, "vmb_sample: need 1 <= n1, n2 and n1+n2 <= 32");
-  if (!a->rgbs || !a->depths || !a->t_wc || !a->bbox || !a->n_keyframes || !a->latest_kf || !a->rays_dir ||
+  const bool shared = a->store_rgbx != nullptr;
+  if (shared && (!a->store_depth || !a->store_inst || !a->store_t_wc || !a->kf_slot || !a->kf_bbox || !a->obj_id ||
+                 a->kf_stride <= 0))
+    return fail(h, VMB_E_ARG, "vmb_sample: shared keyframe store needs depth/inst/t_wc/kf_slot/kf_bbox/obj_id/kf_stride");
+  if (!shared && (!a->rgbs || !a->depths || !a->t_wc || !a->bbox))
+    return fail(h, VMB_E_ARG, "vmb_sample: missing per-object keyframe pointer tables");
+  if (!a->n_keyframes || !a->latest_kf || !a->rays_dir ||
       !a->bin_limits || !a->pcs || !a->z_vals || !a->gt_depth || !a->gt_colour || !a->sem || !a->mask_depth)
     return fail(h, VMB_E_ARG, "vmb_sample: missing tensor pointer");
   SampleParams p;
@@ -290,7 +300,34 @@ int vmb_sample(vmb_handle* h, const vmb_sample_args* a, void* stream) {
   p.inj_kf = a->inj_kf; p.inj_u_w = a->inj_u_w; p.inj_u_h = a->inj_u_h; p.inj_u_z = a->inj_u_z; p.inj_nrm = a->inj_nrm;
   p.pcs = a->pcs; p.z = a->z_vals; p.gt_depth = a->gt_depth; p.gt_colour = a->gt_colour; p.rgb_u8 = a->gt_rgb_u8;
   p.sem = a->sem; p.mask = a->mask_depth;
+  p.st_rgbx = reinterpret_cast<const uchar4*>(a->store_rgbx); p.st_depth = a->store_depth; p.st_inst = a->store_inst;
+  p.st_twc = a->store_t_wc; p.kf_slot = a->kf_slot; p.bbox_flat = a->kf_bbox; p.obj_id = a->obj_id; p.kf_stride = a->kf_stride;
   k_sample<<<a->n_obj, 512, 0, (cudaStream_t)stream>>>(p);
+  CUDA_TRY(h, cudaGetLastError());
+  return VMB_OK;
+}
+
+// ---- K4: frame ingest (instance image -> per-instance boxes, shared-store write) ---------------------
+int vmb_ingest_frame(vmb_handle* h, const vmb_ingest_args* a, void* stream) {
+  if (!h || !a || a->width <= 0 || a->height <= 0 || a->max_id <= 0 || !a->inst || !a->stats || !a->bbox)
+    return fail(h, VMB_E_ARG, "vmb_ingest_frame: bad arguments");
+  if (a->bbox_scale < 0.f) return fail(h, VMB_E_ARG, "vmb_ingest_frame: bbox_scale must be >= 0 (utils.py:37)");
+  if (a->bg_class && (!a->cls || a->n_class <= 0))
+    return fail(h, VMB_E_ARG, "vmb_ingest_frame: bg_class needs the class image and n_class");
+  const bool write = a->dst_inst != nullptr;
+  if (write && ((a->rgb != nullptr) != (a->dst_rgbx != nullptr) || (a->depth != nullptr) != (a->dst_depth != nullptr)))
+    return fail(h, VMB_E_ARG, "vmb_ingest_frame: rgb/depth sources and store destinations must come in pairs");
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long n = (long long)a->width * a->height;
+  const int blocks = 2 * h->n_sm;
+  ing::k_ingest_init<<<(a->max_id + 255) / 256, 256, 0, st>>>(a->stats, a->max_id);
+  ing::k_ingest_stats<<<blocks, 256, 0, st>>>(a->inst, a->cls, a->width, a->height, a->max_id, a->stats);
+  ing::k_ingest_finalize<<<(a->max_id + 255) / 256, 256, 0, st>>>(a->stats, a->bbox, a->max_id, a->width, a->height,
+                                                                 (float)(0.5 * (double)a->bbox_scale), a->min_extent,
+                                                                 a->bg_class, a->n_class);
+  if (write)
+    ing::k_ingest_write<<<4 * h->n_sm, 256, 0, st>>>(a->inst, a->rgb, a->depth, a->stats, a->max_id, n,
+                                                     reinterpret_cast<uchar4*>(a->dst_rgbx), a->dst_depth, a->dst_inst);
   CUDA_TRY(h, cudaGetLastError());
   return VMB_OK;
 }

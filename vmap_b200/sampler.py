@@ -57,9 +57,45 @@ class BatchedSampler:
         except Exception:
             pass
 
+    def _outputs(self, B, N, S, want_u8):
+        dev = self.device
+        out = {
+            "pcs": torch.empty(B, N, S, 3, dtype=torch.float32, device=dev),
+            "z": torch.empty(B, N, S, dtype=torch.float32, device=dev),
+            "gt_depth": torch.empty(B, N, dtype=torch.float32, device=dev),
+            "gt_colour": torch.empty(B, N, 3, dtype=torch.float32, device=dev),
+            "sem": torch.empty(B, N, dtype=torch.uint8, device=dev),
+            "mask_depth": torch.empty(B, N, dtype=torch.bool, device=dev),
+        }
+        if want_u8:
+            out["gt_rgb_u8"] = torch.empty(B, N, 3, dtype=torch.uint8, device=dev)
+        return out
+
+    def _launch(self, a, out, B, n_frames, n_pix, W, H, rays_dir, seed, offset, inject, keep):
+        dev = self.device
+        a.n_obj, a.n_frames, a.n_pix = B, n_frames, n_pix
+        a.n_bins_cam2surface, a.n_bins, a.width, a.height = self.n1, self.n2, W, H
+        a.min_bound, a.surface_eps, a.stop_eps = self.min_bound, self.eps, self.oeps
+        a.rays_dir, a.bin_limits = _p(rays_dir), _p(self.bin_limits)
+        a.seed, a.offset = seed, offset
+        inj = None
+        if inject is not None:
+            inj = {k: v.to(dev).contiguous() for k, v in inject.items()}
+            a.inj_kf, a.inj_u_w, a.inj_u_h = _p(inj["kf"]), _p(inj["u_w"]), _p(inj["u_h"])
+            a.inj_u_z, a.inj_nrm = _p(inj["u_z"]), _p(inj["nrm"])
+        a.pcs, a.z_vals, a.gt_depth, a.gt_colour = _p(out["pcs"]), _p(out["z"]), _p(out["gt_depth"]), _p(out["gt_colour"])
+        a.gt_rgb_u8 = _p(out.get("gt_rgb_u8"))
+        a.sem, a.mask_depth = _p(out["sem"]), _p(out["mask_depth"])
+        with torch.cuda.device(dev):
+            _lib.check(self._handle, self.lib.vmb_sample(
+                self._handle, C.byref(a), C.c_void_p(torch.cuda.current_stream().cuda_stream)), "vmb_sample")
+        self._keep = (inj, keep)      # alive until the next call (async launch)
+        return out
+
     def sample(self, objects: List[KeyframeSet], n_frames: int, n_pix: int, rays_dir: torch.Tensor,
                seed: int = 0, offset: int = 0, inject: Optional[Dict[str, torch.Tensor]] = None,
                want_u8: bool = False) -> Dict[str, torch.Tensor]:
+        """Per-object keyframe buffers (the reference's layout, vmap.py:137-176)."""
         dev = self.device
         B = len(objects)
         N, S = n_frames * n_pix, self.n1 + self.n2
@@ -72,37 +108,59 @@ class BatchedSampler:
         ptrs = torch.tensor([[o.rgbs_batch.data_ptr(), o.depth_batch.data_ptr(), o.t_wc_batch.data_ptr(),
                               o.bbox.data_ptr()] for o in objects], dtype=torch.int64).t().contiguous().to(dev)
         nkf = torch.tensor([o.n_keyframes for o in objects], dtype=torch.int32, device=dev)
-        latest = torch.tensor([(list(o.latest_kf) + [0, 0])[:2] if len(o.latest_kf) >= 2
-                               else [o.latest_kf[0] if len(o.latest_kf) else 0] * 2 for o in objects],
-                              dtype=torch.int32, device=dev)
-        out = {
-            "pcs": torch.empty(B, N, S, 3, dtype=torch.float32, device=dev),
-            "z": torch.empty(B, N, S, dtype=torch.float32, device=dev),
-            "gt_depth": torch.empty(B, N, dtype=torch.float32, device=dev),
-            "gt_colour": torch.empty(B, N, 3, dtype=torch.float32, device=dev),
-            "sem": torch.empty(B, N, dtype=torch.uint8, device=dev),
-            "mask_depth": torch.empty(B, N, dtype=torch.bool, device=dev),
-        }
-        if want_u8:
-            out["gt_rgb_u8"] = torch.empty(B, N, 3, dtype=torch.uint8, device=dev)
+        latest = torch.tensor([_latest2(o.latest_kf) for o in objects], dtype=torch.int32, device=dev)
+        out = self._outputs(B, N, S, want_u8)
         a = _lib.SampleArgs()
-        a.n_obj, a.n_frames, a.n_pix = B, n_frames, n_pix
-        a.n_bins_cam2surface, a.n_bins, a.width, a.height = self.n1, self.n2, W, H
-        a.min_bound, a.surface_eps, a.stop_eps = self.min_bound, self.eps, self.oeps
         a.rgbs, a.depths, a.t_wc, a.bbox = _p(ptrs[0]), _p(ptrs[1]), _p(ptrs[2]), _p(ptrs[3])
         a.n_keyframes, a.latest_kf = _p(nkf), _p(latest)
-        a.rays_dir, a.bin_limits = _p(rays_dir), _p(self.bin_limits)
-        a.seed, a.offset = seed, offset
-        if inject is not None:
-            inj = {k: v.to(dev).contiguous() for k, v in inject.items()}
-            a.inj_kf, a.inj_u_w, a.inj_u_h = _p(inj["kf"]), _p(inj["u_w"]), _p(inj["u_h"])
-            a.inj_u_z, a.inj_nrm = _p(inj["u_z"]), _p(inj["nrm"])
-            self._keep = inj
-        a.pcs, a.z_vals, a.gt_depth, a.gt_colour = _p(out["pcs"]), _p(out["z"]), _p(out["gt_depth"]), _p(out["gt_colour"])
-        a.gt_rgb_u8 = _p(out.get("gt_rgb_u8"))
-        a.sem, a.mask_depth = _p(out["sem"]), _p(out["mask_depth"])
-        with torch.cuda.device(dev):
-            _lib.check(self._handle, self.lib.vmb_sample(
-                self._handle, C.byref(a), C.c_void_p(torch.cuda.current_stream().cuda_stream)), "vmb_sample")
-        self._keep = (self._keep, ptrs, nkf, latest)      # alive until the next call (async launch)
+        return self._launch(a, out, B, n_frames, n_pix, W, H, rays_dir, seed, offset, inject, (ptrs, nkf, latest))
+
+    def sample_store(self, store, tables: "KeyframeTables", n_frames: int, n_pix: int, rays_dir: torch.Tensor,
+                     seed: int = 0, offset: int = 0, inject: Optional[Dict[str, torch.Tensor]] = None,
+                     want_u8: bool = False) -> Dict[str, torch.Tensor]:
+        """Shared keyframe store (keyframes.FrameStore): frames stored once, per-object (slot, bbox) tables,
+        pixel state derived from the instance image.  Same draws / outputs as ``sample`` on per-object copies."""
+        dev = self.device
+        assert store.device == dev
+        B, KF = tables.kf_slot.shape
+        N, S = n_frames * n_pix, self.n1 + self.n2
+        t = tables.to_device(dev)
+        out = self._outputs(B, N, S, want_u8)
+        a = _lib.SampleArgs()
+        a.store_rgbx, a.store_depth, a.store_inst, a.store_t_wc = _p(store.rgbx), _p(store.depth), _p(store.inst), _p(store.t_wc)
+        a.kf_slot, a.kf_bbox, a.obj_id, a.kf_stride = _p(t["kf_slot"]), _p(t["kf_bbox"]), _p(t["obj_id"]), KF
+        a.n_keyframes, a.latest_kf = _p(t["n_kf"]), _p(t["latest"])
+        return self._launch(a, out, B, n_frames, n_pix, store.W, store.H, rays_dir, seed, offset, inject, t)
+
+
+def _latest2(q):
+    q = list(q)
+    return q[-2:] if len(q) >= 2 else [q[0] if q else 0] * 2
+
+
+class KeyframeTables:
+    """Host-side per-object keyframe tables of the shared store, packed into ONE pinned buffer so a frame's
+    sampling needs a single small host->device copy (instead of B x 4 pointer-table entries)."""
+
+    def __init__(self, kf_slot, kf_bbox, obj_id, n_kf, latest):
+        self.kf_slot = torch.as_tensor(kf_slot, dtype=torch.int32).contiguous()          # [B,KF]
+        self.kf_bbox = torch.as_tensor(kf_bbox, dtype=torch.float32).contiguous()        # [B,KF,4]
+        self.obj_id = torch.as_tensor(obj_id, dtype=torch.int32).contiguous()            # [B]
+        self.n_kf = torch.as_tensor(n_kf, dtype=torch.int32).contiguous()                # [B]
+        self.latest = torch.as_tensor(latest, dtype=torch.int32).contiguous()            # [B,2]
+        B, KF = self.kf_slot.shape
+        assert self.kf_bbox.shape == (B, KF, 4) and self.obj_id.shape == (B,) and self.latest.shape == (B, 2)
+
+    def to_device(self, dev):
+        parts = [("kf_slot", self.kf_slot), ("kf_bbox", self.kf_bbox.view(torch.int32)), ("obj_id", self.obj_id),
+                 ("n_kf", self.n_kf), ("latest", self.latest)]
+        flat = torch.cat([t.reshape(-1) for _, t in parts])
+        if torch.cuda.is_available():
+            flat = flat.pin_memory()
+        d = flat.to(dev, non_blocking=True)
+        out, o = {"_flat": d, "_host": flat}, 0
+        for name, t in parts:
+            v = d[o:o + t.numel()]
+            out[name] = v.view(torch.float32) if name == "kf_bbox" else v
+            o += t.numel()
         return out

@@ -17,7 +17,7 @@ from typing import Dict, List, Optional
 import torch
 
 from . import trainer as trainer_mod
-from .sampler import BatchedSampler, KeyframeSet
+from .sampler import BatchedSampler, KeyframeSet, KeyframeTables, _latest2
 
 
 class performance_measure:
@@ -81,27 +81,49 @@ def sample_all(objects: List["sceneObject"], n_frames: int, n_samples: int, cach
     _CALLS[0] += 1
     if seed is None:
         seed = torch.initial_seed() & 0x7FFFFFFFFFFFFFFF
+    store = objects[0].store
+    if store is not None:                                  # shared keyframe store: (slot, bbox) tables only
+        assert all(o.store is store for o in objects), "objects of one launch must share the FrameStore"
+        return smp.sample_store(store, keyframe_tables(objects), n_frames, n_samples, cached_rays_dir,
+                                seed=seed, offset=_CALLS[0])
     return smp.sample([o.keyframe_set() for o in objects], n_frames, n_samples, cached_rays_dir,
                       seed=seed, offset=_CALLS[0])
+
+
+def keyframe_tables(objects: List["sceneObject"]) -> KeyframeTables:
+    """Pack the (store slot, bbox) tables of shared-store objects for one sampler launch."""
+    return KeyframeTables(torch.tensor([o.kf_store_slot for o in objects], dtype=torch.int32),
+                          torch.stack([o.bbox for o in objects]),
+                          [int(o.obj_id) for o in objects], [o.n_keyframes for o in objects],
+                          [_latest2(o.lastest_kf_queue[-2:] if len(o.lastest_kf_queue) >= 2 else [0, 0])
+                           for o in objects])
 
 
 class sceneObject:
     """Per-object keyframe buffers + sampler entry point (vmap.py:90-491)."""
 
-    def __init__(self, cfg, obj_id, rgb: torch.Tensor, depth: torch.Tensor, mask: torch.Tensor,
-                 bbox_2d: torch.Tensor, t_wc: torch.Tensor, live_frame_id) -> None:
+    def __init__(self, cfg, obj_id, rgb: Optional[torch.Tensor], depth: Optional[torch.Tensor],
+                 mask: Optional[torch.Tensor], bbox_2d: torch.Tensor, t_wc: torch.Tensor, live_frame_id,
+                 store=None, frame_slot: Optional[int] = None) -> None:
+        """``store`` / ``frame_slot``: shared keyframe store mode (keyframes.FrameStore) -- the frame already
+        lives in ``store`` slot ``frame_slot``; rgb / depth / mask are not copied (pass None) and the object
+        keeps only (slot, bbox) per keyframe.  Without ``store`` this is the reference's per-object layout."""
         self.do_bg = cfg.do_bg
         self.obj_id = obj_id
         self.data_device = cfg.data_device
         self.training_device = cfg.training_device
-        assert rgb.shape[:2] == depth.shape and rgb.shape[:2] == mask.shape
+        self.store = store
+        if store is None:
+            assert rgb.shape[:2] == depth.shape and rgb.shape[:2] == mask.shape
+        else:
+            assert frame_slot is not None
         assert bbox_2d.shape == (4,) and t_wc.shape == (4, 4)
         bg = self.do_bg and self.obj_id == 0                     # vmap.py:109-118
         self.obj_scale = cfg.bg_scale if bg else cfg.obj_scale
         self.hidden_feature_size = cfg.hidden_feature_size_bg if bg else cfg.hidden_feature_size
         self.n_bins_cam2surface = cfg.n_bins_cam2surface_bg if bg else cfg.n_bins_cam2surface
         self.keyframe_step = cfg.keyframe_step_bg if bg else cfg.keyframe_step
-        self.frames_width, self.frames_height = rgb.shape[0], rgb.shape[1]
+        self.frames_width, self.frames_height = (store.W, store.H) if store is not None else (rgb.shape[0], rgb.shape[1])
         self.min_bound, self.max_bound = cfg.min_depth, cfg.max_depth
         self.n_bins, self.n_unidir_funcs = cfg.n_bins, cfg.n_unidir_funcs
         self.surface_eps, self.stop_eps = cfg.surface_eps, cfg.stop_eps
@@ -113,13 +135,19 @@ class sceneObject:
         self.frame_cnt = 0
         self.lastest_kf_queue = []
         KF, W, H, dev = self.keyframe_buffer_size, self.frames_width, self.frames_height, self.data_device
-        self.bbox = torch.empty(KF, 4, device=dev)               # [u low, u high, v low, v high]
         self.rgb_idx, self.state_idx = slice(0, 3), slice(3, 4)
-        self.rgbs_batch = torch.empty(KF, W, H, 4, dtype=torch.uint8, device=dev)
         self.other_obj, self.this_obj, self.unknown_obj = 0, 1, 2
-        self.depth_batch = torch.empty(KF, W, H, dtype=torch.float32, device=dev)
-        self.t_wc_batch = torch.empty(KF, 4, 4, dtype=torch.float32, device=dev)
-        self._store(0, rgb, depth, mask, bbox_2d, t_wc)
+        if store is None:
+            self.bbox = torch.empty(KF, 4, device=dev)           # [u low, u high, v low, v high]
+            self.rgbs_batch = torch.empty(KF, W, H, 4, dtype=torch.uint8, device=dev)
+            self.depth_batch = torch.empty(KF, W, H, dtype=torch.float32, device=dev)
+            self.t_wc_batch = torch.empty(KF, 4, 4, dtype=torch.float32, device=dev)
+        else:                                                    # host tables only: KF x (slot, bbox)
+            self.bbox = torch.zeros(KF, 4)
+            self.kf_store_slot = [0] * KF                        # unused entries point at slot 0 (never sampled)
+            self._held = [False] * KF
+            self.rgbs_batch = self.depth_batch = self.t_wc_batch = None
+        self._store(0, rgb, depth, mask, bbox_2d, t_wc, frame_slot)
         tcfg = copy.deepcopy(cfg)
         tcfg.obj_id, tcfg.hidden_feature_size, tcfg.obj_scale = self.obj_id, self.hidden_feature_size, self.obj_scale
         self.trainer = trainer_mod.Trainer(tcfg)
@@ -127,7 +155,15 @@ class sceneObject:
         self.pc = []
         self.obj_center = torch.tensor(0.0)
 
-    def _store(self, slot, rgb, depth, mask, bbox_2d, t_wc):
+    def _store(self, slot, rgb, depth, mask, bbox_2d, t_wc, frame_slot=None):
+        if self.store is not None:
+            assert frame_slot is not None, "shared-store object: pass frame_slot"
+            self.store.acquire(frame_slot)
+            if self._held[slot]:
+                self.store.release(self.kf_store_slot[slot])
+            self.kf_store_slot[slot], self._held[slot] = int(frame_slot), True
+            self.bbox[slot] = torch.as_tensor(bbox_2d, dtype=torch.float32).cpu()
+            return
         self.rgbs_batch[slot, :, :, self.rgb_idx] = rgb
         self.rgbs_batch[slot, :, :, self.state_idx] = mask[..., None]
         self.depth_batch[slot] = depth
@@ -139,30 +175,40 @@ class sceneObject:
             del self.kf_id_dict[k]
         self.kf_id_dict[frame_id] = slot
 
-    def append_keyframe(self, rgb, depth, mask, bbox_2d, t_wc, frame_id=1):
+    def release_frames(self):
+        """Shared-store mode: give the object's frame references back (object deleted)."""
+        if self.store is not None:
+            for k, held in enumerate(self._held):
+                if held:
+                    self.store.release(self.kf_store_slot[k])
+                    self._held[k] = False
+
+    def append_keyframe(self, rgb, depth, mask, bbox_2d, t_wc, frame_id=1, frame_slot=None):
         """vmap.py:208-263: a new keyframe every ``keyframe_step`` frames, otherwise the newest
-        slot is overwritten; once the buffer is full a random old keyframe is recycled."""
-        assert rgb.shape[:2] == depth.shape and rgb.shape[:2] == mask.shape
+        slot is overwritten; once the buffer is full a random old keyframe is recycled.
+        Shared-store mode: pass ``frame_slot`` (rgb / depth / mask may be None)."""
         assert bbox_2d.shape == (4,) and t_wc.shape == (4, 4)
         assert self.n_keyframes <= self.keyframe_buffer_size - 1
-        assert rgb.dtype == torch.uint8 and mask.dtype == torch.uint8 and depth.dtype == torch.float32
+        if self.store is None:
+            assert rgb.shape[:2] == depth.shape and rgb.shape[:2] == mask.shape
+            assert rgb.dtype == torch.uint8 and mask.dtype == torch.uint8 and depth.dtype == torch.float32
         is_kf = (self.frame_cnt % self.keyframe_step == 0) or self.n_keyframes == 1
         if self.n_keyframes == self.keyframe_buffer_size - 1:
             self.kf_buffer_full = True
             if self.kf_pointer is None:
                 self.kf_pointer = self.n_keyframes
-            self._store(self.kf_pointer, rgb, depth, mask, bbox_2d, t_wc)
+            self._store(self.kf_pointer, rgb, depth, mask, bbox_2d, t_wc, frame_slot)
             self._slot_to_frame(self.kf_pointer, frame_id)
             if is_kf:
                 self.lastest_kf_queue.append(self.kf_pointer)
                 _, self.kf_pointer = self.prune_keyframe()
                 print("pruned kf id ", self.kf_pointer)
         elif not is_kf:
-            self._store(self.n_keyframes - 1, rgb, depth, mask, bbox_2d, t_wc)
+            self._store(self.n_keyframes - 1, rgb, depth, mask, bbox_2d, t_wc, frame_slot)
             self._slot_to_frame(self.n_keyframes - 1, frame_id)
         else:
             self.kf_id_dict[frame_id] = self.n_keyframes
-            self._store(self.n_keyframes, rgb, depth, mask, bbox_2d, t_wc)
+            self._store(self.n_keyframes, rgb, depth, mask, bbox_2d, t_wc, frame_slot)
             self.lastest_kf_queue.append(self.n_keyframes)
             self.n_keyframes += 1
         self.frame_cnt += 1
@@ -181,8 +227,13 @@ class sceneObject:
         [F*P] bool, obj_labels [F*P] u8, pcs [F,P,S,3], z [F,P,S]."""
         smp = _sampler_for(self)
         _CALLS[0] += 1
-        o = smp.sample([self.keyframe_set()], n_frames, n_samples, cached_rays_dir,
-                       seed=torch.initial_seed() & 0x7FFFFFFFFFFFFFFF, offset=_CALLS[0], want_u8=True)
+        seed = torch.initial_seed() & 0x7FFFFFFFFFFFFFFF
+        if self.store is not None:
+            o = smp.sample_store(self.store, keyframe_tables([self]), n_frames, n_samples, cached_rays_dir,
+                                 seed=seed, offset=_CALLS[0], want_u8=True)
+        else:
+            o = smp.sample([self.keyframe_set()], n_frames, n_samples, cached_rays_dir,
+                           seed=seed, offset=_CALLS[0], want_u8=True)
         S = o["z"].shape[-1]
         return (o["gt_rgb_u8"][0].view(n_frames, n_samples, 3), o["gt_depth"][0].view(n_frames, n_samples),
                 o["mask_depth"][0], o["sem"][0], o["pcs"][0].view(n_frames, n_samples, S, 3),
