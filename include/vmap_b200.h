@@ -237,7 +237,8 @@ int vmb_ingest_frame(vmb_handle* h, const vmb_ingest_args* a, void* stream);
 /* ---- bring-up / test hook (not part of the reference-facing surface) --------------------------- */
 /* Generic tcgen05 GEMM of the layer-wise wide-model path: D[M][N] = A[M][K1+K2] * B[N][K]^T, fp16 in,
  * fp32 accumulate.  a_mn/b_mn = 0: operand stored [rows][ld] with K contiguous; 1: stored [K][ld] with
- * M/N contiguous.  epi 0: out16 = relu(acc*scale + bias); 2: out32 (=|+=) acc*scale; 3: atomicAdd.   */
+ * M/N contiguous.  epi 0: out16 = relu(acc*scale + bias); 2: out32 (=|+=) acc*scale; 3: atomicAdd;
+ * epi + 16 selects the weight-stationary kernel (a_mn = 0, N <= 256).                                */
 int vmb_debug_gemm(int a_mn, int b_mn, int epi, int M, int N, int K1, int K2, const void* a1, long long a1_ld,
                    const void* a2, long long a2_ld, const void* b, long long b_ld, const float* bias, void* out16,
                    int ldo, float* out32, int ld32, int accumulate, int ksplit, float scale, void* stream);

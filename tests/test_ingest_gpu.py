@@ -151,3 +151,60 @@ def test_frame_store_refcounts_and_capacity():
     st.acquire(s1); st.release(s1); assert st.n_used == 3
     st.release(s1); assert st.n_used == 2
     assert st.put(*z()) == s1
+
+
+def test_frame_loop_with_shared_store_trains():
+    """train.py:104-141,195-326 with the shared store: ingest -> objects from the kept instances ->
+    sample_all (one launch, store mode) -> fused step.  Loss finite and decreasing, references consistent."""
+    import types
+    from vmap_b200 import vmap as vm
+    from vmap_b200 import synth
+    from vmap_b200.ensemble import VmapEnsemble
+    W, H = 160, 120
+    cfg = types.SimpleNamespace(do_bg=False, data_device=DEV, training_device=DEV, obj_scale=2.0, bg_scale=5.0,
+                                hidden_feature_size=32, hidden_feature_size_bg=128, n_bins_cam2surface=1,
+                                n_bins_cam2surface_bg=5, keyframe_step=2, keyframe_step_bg=5, min_depth=0.0,
+                                max_depth=8.0, n_bins=9, n_unidir_funcs=5, surface_eps=0.1, stop_eps=0.05,
+                                keyframe_buffer_size=5, W=W, H=H, fx=100.0, fy=100.0, cx=W / 2 - 0.5, cy=H / 2 - 0.5,
+                                n_unidir=5)
+    real_trainer = vm.trainer_mod.Trainer
+    vm.trainer_mod.Trainer = lambda c: types.SimpleNamespace()
+    try:
+        st = _store(W, H, cap=16)
+        cam = vm.cameraInfo(cfg)
+        inst, cls = io.synthetic_instance_frame(W, H, 14, seed=21)
+        objs = {}
+        rng = np.random.default_rng(1)
+        for fid in range(9):
+            rgb = torch.from_numpy(rng.integers(0, 255, (W, H, 3), dtype=np.uint8))
+            depth = torch.from_numpy((rng.random((W, H), dtype=np.float32) * 2 + 1).astype(np.float32))
+            T = torch.eye(4); T[0, 3] = 0.01 * fid
+            slot, _, _ = st.ingest(rgb, depth, torch.from_numpy(inst), T, frame_id=fid, cls=torch.from_numpy(cls),
+                                   background_cls=[5, 12, 30, 31, 40, 60, 92, 93, 95, 97, 98, 79])
+            for oid, bbox in st.visible_objects().items():
+                if oid == 0:
+                    continue
+                bbox = bbox.cpu()
+                if oid in objs:
+                    objs[oid].append_keyframe(None, None, None, bbox, T, fid, frame_slot=slot)
+                else:
+                    objs[oid] = vm.sceneObject(cfg, oid, None, None, None, bbox, T, fid, store=st, frame_slot=slot)
+            st.release(slot)
+        olist = list(objs.values())
+        assert len(olist) >= 3 and st.n_used <= 9       # objects prune independently: <= frames seen
+        refs = sum(sum(o._held) for o in olist)
+        assert sum(st.refcount) == refs
+        ens = VmapEnsemble(len(olist), hidden=32, scale=2.0, device=DEV)
+        ens.load_stacked(synth.init_params(len(olist), 32, seed=0))
+        losses = []
+        for it in range(30):
+            batch = vm.sample_all(olist, 10, 12, cam.rays_dir_cache.contiguous(), seed=it)
+            assert set(torch.unique(batch["sem"]).tolist()) <= {0, 1, 2} and bool((batch["sem"] == 1).any())
+            losses.append(float(ens.step(batch)))
+        ens.check_status()
+        assert all(np.isfinite(losses)) and np.mean(losses[-5:]) < np.mean(losses[:5])
+        for o in olist:
+            o.release_frames()
+        assert st.n_used == 0
+    finally:
+        vm.trainer_mod.Trainer = real_trainer

@@ -299,18 +299,48 @@ __global__ void __launch_bounds__(256) k_lw_colsum(const __half* __restrict__ dY
 // ---------------------------------------------------------------------------------------------
 // PE backward: d/d(proj_d) = pi sum_k 2^k g[k,d] cos(pi 2^k proj_d);  dB[d][i] += dproj_d * t_i
 // ---------------------------------------------------------------------------------------------
+constexpr int PEB_LD = 145;      // odd row stride (floats): per-thread row reads are bank-conflict free
+constexpr int PEB_SMEM = 128 * PEB_LD * 4;
 __global__ void __launch_bounds__(128) k_lw_pe_bwd(const float* __restrict__ pcs, const float* __restrict__ dirs,
                                                    const float* __restrict__ scale_ptr, long long P,
                                                    const float* __restrict__ dE, float* __restrict__ gB) {
+  extern __shared__ float sg[];                 // [128 points][PEB_LD]: the dE rows of this block, staged coalesced
   const float scale = *scale_ptr;
-  __shared__ float sdp[VMB_NDIRS][129];
   __shared__ float st[3][129];
-  const long long p = (long long)blockIdx.x * 128 + threadIdx.x;
+  const long long p0 = (long long)blockIdx.x * 128;
+  const long long p = p0 + threadIdx.x;
+  {
+    // the block's 128 dE rows are one contiguous 128 x 576 B span: flat float4 loads, 12 in flight per thread
+    const long long rows = min(128LL, P - p0);
+    const int n4 = (int)rows * (EW / 4);
+    const float4* src = reinterpret_cast<const float4*>(dE + p0 * EW);
+#pragma unroll 1
+    for (int base = 0; base < n4; base += 12 * 128) {
+      float4 q[12];
+#pragma unroll
+      for (int u = 0; u < 12; ++u) {
+        const int i = base + u * 128 + threadIdx.x;
+        q[u] = i < n4 ? src[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < 12; ++u) {
+        const int i = base + u * 128 + threadIdx.x;
+        if (i < n4) {
+          const int r = i / (EW / 4), c = (i - r * (EW / 4)) * 4;
+          float* d = sg + r * PEB_LD + c;
+          d[0] = q[u].x; d[1] = q[u].y; d[2] = q[u].z; d[3] = q[u].w;
+        }
+      }
+    }
+  }
   float t0 = 0.f, t1 = 0.f, t2 = 0.f;
   const bool ok = p < P;
   if (ok) { t0 = pcs[p * 3] / scale; t1 = pcs[p * 3 + 1] / scale; t2 = pcs[p * 3 + 2] / scale; }
   st[0][threadIdx.x] = t0; st[1][threadIdx.x] = t1; st[2][threadIdx.x] = t2;
-  const float* g = dE + p * EW;
+  __syncthreads();
+  const float* g = sg + threadIdx.x * PEB_LD;
+  float dpv[VMB_NDIRS];
+#pragma unroll
   for (int d = 0; d < VMB_NDIRS; ++d) {
     float dp = 0.f;
     if (ok) {
@@ -324,13 +354,16 @@ __global__ void __launch_bounds__(128) k_lw_pe_bwd(const float* __restrict__ pcs
       dp = fmaf(32.f * g[E1W + VMB_NDIRS + d], c[5], dp);
       dp *= VMB_PI_F * INV_LS;
     }
-    sdp[d][threadIdx.x] = dp;
+    dpv[d] = dp;
   }
+  __syncthreads();                               // everyone is done reading its dE row: reuse sg as [21][129]
+#pragma unroll
+  for (int d = 0; d < VMB_NDIRS; ++d) sg[d * 129 + threadIdx.x] = dpv[d];
   __syncthreads();
   if (threadIdx.x < VMB_NDIRS * 3) {
     const int d = threadIdx.x / 3, i = threadIdx.x - d * 3;
     float s = 0.f;
-    for (int q = 0; q < 128; ++q) s = fmaf(sdp[d][q], st[i][q], s);
+    for (int q = 0; q < 128; ++q) s = fmaf(sg[d * 129 + q], st[i][q], s);
     atomicAdd(gB + threadIdx.x, s);
   }
 }
@@ -361,7 +394,7 @@ static int step_object(Workspace& ws, const VmbLayout& L, const StepParams& sp, 
   auto fwd = [&](const Operand& a1, const Operand& a2, int K1, int K2, long long woff, int ldw, int boff, __half* out) {
     GemmArgs g; memset(&g, 0, sizeof(g));
     g.M = (int)np; g.N = H; g.K1 = K1; g.K2 = K2; g.bias = Pb + boff; g.out16 = out; g.ldo = H; g.scale = 1.0f;
-    return launch_gemm<0, 0, EPI_RELU_F16>(a1, a2, Operand{Wi + woff, H, ldw, ldw}, g, mt, (H + BN - 1) / BN, 1, st);
+    return launch_gemm_auto<0, EPI_RELU_F16>(a1, a2, Operand{Wi + woff, H, ldw, ldw}, g, mt, (H + BN - 1) / BN, st);
   };
   LW_TRY(fwd(opE1, none, E1W, 0, 0, 96, L.o_bin, ws.X1));
   LW_TRY(fwd(opX(ws.X1), none, H, 0, off_m1(H), H, L.o_bm1, ws.X2));
@@ -394,12 +427,12 @@ static int step_object(Workspace& ws, const VmbLayout& L, const StepParams& sp, 
     GemmArgs g; memset(&g, 0, sizeof(g));
     g.M = (int)np; g.N = H; g.K1 = H; g.out16 = out; g.ldo = H; g.gate = xprev; g.ldg = H; g.r1_row = r1row; g.r1_col = r1col;
     g.r1_stride = 1; g.scale = 1.0f;
-    return launch_gemm<0, 1, EPI_GATE_F16>(Operand{dY, np, H, H}, none, Operand{Wi + woff, H, H, ldw}, g, mt, (H + BN - 1) / BN, 1, st);
+    return launch_gemm_auto<1, EPI_GATE_F16>(Operand{dY, np, H, H}, none, Operand{Wi + woff, H, H, ldw}, g, mt, (H + BN - 1) / BN, st);
   };
   auto dgrad_emb = [&](const __half* dY, long long woff, int ldw, int N, int ecol, int accumulate) {
     GemmArgs g; memset(&g, 0, sizeof(g));
     g.M = (int)np; g.N = N; g.K1 = H; g.out32 = ws.dE + ecol; g.ld32 = EW; g.accumulate = accumulate; g.scale = 1.0f;
-    return launch_gemm<0, 1, EPI_F32>(Operand{dY, np, H, H}, none, Operand{Wi + woff, H, N, ldw}, g, mt, 1, 1, st);
+    return launch_gemm_auto<1, EPI_F32>(Operand{dY, np, H, H}, none, Operand{Wi + woff, H, N, ldw}, g, mt, 1, st);
   };
   // heads: dW_a[o] = sum_p d_a fc4[p][o]; dW_oc[c][o] = sum_p d_rc[c] hc[p][o]   (B = dh16 [P][8], columns 0 / 1..3)
   {
@@ -422,16 +455,34 @@ static int step_object(Workspace& ws, const VmbLayout& L, const StepParams& sp, 
   // cat_layer
   LW_TRY(wgrad(ws.dYb, opX(ws.X2), H, L.o_Wcat, H + VMB_E1, H, -1, -1));
   LW_TRY(wgrad(ws.dYb, opE1, E1W, L.o_Wcat + H, H + VMB_E1, VMB_E1, ONES1, L.o_bcat));
-  LW_TRY(dgrad_emb(ws.dYb, off_cat(H) + H, H + 96, E1W, 0, 0));
-  LW_TRY(dgrad_gate(ws.dYb, off_cat(H), H + 96, ws.X2, ws.dYa, nullptr, nullptr));                  // dY2 -> dYa
+  LW_TRY(dgrad_gate(ws.dYb, off_cat(H), H + 96, ws.X2, ws.dYa, nullptr, nullptr));                  // dY2 -> dYa (dY3 stays in dYb)
   // mid1
   LW_TRY(wgrad(ws.dYa, opX(ws.X1), H, L.o_Wm1, H, H, -1, -1));
   k_lw_colsum<<<(int)((np + 511) / 512), 256, 0, st>>>(ws.dYa, np, H, G + L.o_bm1);
-  LW_TRY(dgrad_gate(ws.dYa, off_m1(H), H, ws.X1, ws.dYb, nullptr, nullptr));                        // dY1 -> dYb
+  LW_TRY(dgrad_gate(ws.dYa, off_m1(H), H, ws.X1, ws.dYc, nullptr, nullptr));                        // dY1 -> dYc (free since color_linear)
   // in_layer
-  LW_TRY(wgrad(ws.dYb, opE1, E1W, L.o_Win, VMB_E1, VMB_E1, ONES1, L.o_bin));
-  LW_TRY(dgrad_emb(ws.dYb, 0, 96, E1W, 0, 1));
-  k_lw_pe_bwd<<<nblk, 128, 0, st>>>(pcs, dirs, scale_p, np, ws.dE, G + L.o_B);
+  LW_TRY(wgrad(ws.dYc, opE1, E1W, L.o_Win, VMB_E1, VMB_E1, ONES1, L.o_bin));
+  // d emb1 = dY3 @ W_cat[:, H:] + dY1 @ W_in in ONE launch: A = [dY3 | dY1] along K, B = the two weight blocks
+  {
+    GemmArgs g; memset(&g, 0, sizeof(g));
+    g.M = (int)np; g.N = E1W; g.K1 = H; g.K2 = H; g.out32 = ws.dE; g.ld32 = EW; g.accumulate = 0; g.scale = 1.0f;
+    const Operand bcat{Wi + off_cat(H) + H, H, E1W, H + 96}, bin{Wi, H, E1W, 96};
+    cudaError_t e = launch_gemm_ws<1, EPI_F32>(Operand{ws.dYb, np, H, H}, Operand{ws.dYc, np, H, H}, bcat, g, mt, st, &bin);
+    if (e == cudaErrorNotSupported) {
+      (void)cudaGetLastError();
+      LW_TRY(dgrad_emb(ws.dYb, off_cat(H) + H, H + 96, E1W, 0, 0));
+      LW_TRY(dgrad_emb(ws.dYc, 0, 96, E1W, 0, 1));
+    } else LW_TRY(e);
+  }
+  {
+    static bool attr_set[64] = {};
+    int dev = 0; cudaGetDevice(&dev);
+    if (!attr_set[dev & 63]) {
+      LW_TRY(cudaFuncSetAttribute(k_lw_pe_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, PEB_SMEM));
+      attr_set[dev & 63] = true;
+    }
+  }
+  k_lw_pe_bwd<<<nblk, 128, PEB_SMEM, st>>>(pcs, dirs, scale_p, np, ws.dE, G + L.o_B);
   LW_TRY(cudaGetLastError());
   return 0;
 }

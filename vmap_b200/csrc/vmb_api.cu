@@ -340,6 +340,8 @@ int vmb_debug_gemm(int a_mn, int b_mn, int epi, int M, int N, int K1, int K2, co
                    float* out32, int ld32, int accumulate, int ksplit, float scale, void* stream) {
   using namespace lw;
   const int K = K1 + K2;
+  const bool ws = (epi & 16) != 0;             // +16: weight-stationary kernel (no fallback: the test wants THAT kernel)
+  epi &= 15;
   Operand A1{a1, a_mn ? K1 : M, a_mn ? M : K1, a1_ld};
   Operand A2{a2, a_mn ? K2 : M, a_mn ? M : K2, a2_ld};
   Operand B{b, b_mn ? K : N, b_mn ? N : K, b_ld};
@@ -351,6 +353,11 @@ int vmb_debug_gemm(int a_mn, int b_mn, int epi, int M, int N, int K1, int K2, co
   const int mt = (M + BM - 1) / BM, nt = (N + BN - 1) / BN, z = ksplit > 0 ? (K + ksplit - 1) / ksplit : 1;
   cudaStream_t st = (cudaStream_t)stream;
   cudaError_t e = cudaErrorInvalidValue;
+  if (ws) {
+    if (a_mn == 0 && b_mn == 0 && epi == 0) e = launch_gemm_ws<0, EPI_RELU_F16>(A1, A2, B, g, mt, st);
+    else if (a_mn == 0 && b_mn == 0 && epi == 2) e = launch_gemm_ws<0, EPI_F32>(A1, A2, B, g, mt, st);
+    else if (a_mn == 0 && b_mn == 1 && epi == 2) e = launch_gemm_ws<1, EPI_F32>(A1, A2, B, g, mt, st);
+  } else
   if (a_mn == 0 && b_mn == 0 && epi == 0) e = launch_gemm<0, 0, EPI_RELU_F16>(A1, A2, B, g, mt, nt, z, st);
   else if (a_mn == 0 && b_mn == 0 && epi == 2) e = launch_gemm<0, 0, EPI_F32>(A1, A2, B, g, mt, nt, z, st);
   else if (a_mn == 0 && b_mn == 1 && epi == 2) e = launch_gemm<0, 1, EPI_F32>(A1, A2, B, g, mt, nt, z, st);
