@@ -154,6 +154,9 @@ typedef struct vmb_forward_args {
   const float* params; const float* scale;
   float* alpha;  long long alpha_stride;
   float* colour; long long colour_stride;
+  const void* image;   /* optional fp16 weight image (vmb_image_bytes per object, kept current by vmb_adam /
+                          vmb_build_image): hidden 32 then runs the forward half of the fused tcgen05 kernel,
+                          hidden 64/128/256 the layer-wise tcgen05 GEMMs; NULL = fp32 CUDA-core kernel          */
 } vmb_forward_args;
 
 int vmb_forward(vmb_handle* h, const vmb_forward_args* a, void* stream);

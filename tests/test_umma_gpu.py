@@ -90,3 +90,39 @@ def test_umma_training_tracks_fp32_kernel():
     assert abs(l_a - l_u) < 0.05 * abs(l_a)
     assert rel_l2(lu, la) < 0.15
     u.check_status()
+
+
+@pytest.mark.parametrize("N", [1000, 70001])
+def test_eval_points_tensor_core_forward_matches_oracle(N):
+    """Trainer.eval_points (trainer.py:77-90) through the forward half of the fused tcgen05 kernel."""
+    B = 3
+    params = vo.init_params(B, 32, seed=9)
+    pts = (torch.rand(B, N, 3, generator=torch.Generator().manual_seed(1)) - 0.5) * 4
+    alpha_ref, col_ref = vo.forward(params, torch.full((B,), 2.0), pts.view(B, N, 1, 3))
+    ens = make_ensemble(params, 2.0, 32, impl="umma")
+    alpha, col = ens.eval_points(pts.cuda())
+    a32, c32 = ens.eval_points(pts.cuda(), impl="fp32")
+    assert rel_l2(a32, alpha_ref.view(B, N)) < 1e-5
+    print("eval_points tcgen05 vs oracle: alpha", rel_l2(alpha, alpha_ref.view(B, N)), "colour", rel_l2(col, col_ref.view(B, N, 3)))
+    assert rel_l2(alpha, alpha_ref.view(B, N)) < 2e-3
+    assert rel_l2(col, col_ref.view(B, N, 3)) < 1e-3
+
+
+def test_eval_points_throughput_grid():
+    """256^3-class query (meshing, trainer.py:35-75): tensor-core forward vs the fp32 CUDA-core kernel."""
+    B, N = 4, 128 ** 3
+    params = vo.init_params(B, 32, seed=3)
+    pts = (torch.rand(B, N, 3, device="cuda") - 0.5) * 4
+    ens = make_ensemble(params, 2.0, 32, impl="umma")
+    res = {}
+    for impl in ("umma", "fp32"):
+        for _ in range(2):
+            ens.eval_points(pts, impl=impl)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3):
+            a, c = ens.eval_points(pts, impl=impl)
+        e1.record(); torch.cuda.synchronize()
+        res[impl] = e0.elapsed_time(e1) / 3
+        print(f"eval_points {B} x {N} points, {impl}: {res[impl]:.2f} ms -> {B * N / res[impl] / 1e6:.2f} G points/s")
+    assert res["umma"] < res["fp32"]

@@ -59,6 +59,7 @@ class ForwardArgs(C.Structure):
         ("params", _vp), ("scale", _vp),
         ("alpha", _vp), ("alpha_stride", _ll),
         ("colour", _vp), ("colour_stride", _ll),
+        ("image", _vp),
     ]
 
 

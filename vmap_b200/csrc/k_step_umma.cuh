@@ -360,7 +360,7 @@ k_step_umma(StepParams a, VmbLayout L, const unsigned char* __restrict__ image, 
   if (warp == 15) { ptx::tmem_alloc(&misc->tmem_base, 512); ptx::tmem_relinquish(); }
   if (tid < 3) {                      // render_rays.py:68-73: one empty mask anywhere zeroes the term for all
     int on = 1;
-    for (int i = 0; i < a.B; ++i) on &= (a.counts[i * 4 + tid] != 0);
+    if (!a.fwd_only) for (int i = 0; i < a.B; ++i) on &= (a.counts[i * 4 + tid] != 0);
     misc->on[tid] = on;
   }
   ptx::tc_fence_before();
@@ -412,9 +412,9 @@ k_step_umma(StepParams a, VmbLayout L, const unsigned char* __restrict__ image, 
       const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
       const uint32_t tA = tm + ACC0 + g * ACC_STRIDE + lane_base, tB = tA + 32, tE = tA + 64;
       const float isc = 1.0f / a.scale[b];
-      const float inv_nd = 1.f / ((float)a.counts[b * 4 + 0] + 1e-10f);
-      const float inv_no = 1.f / ((float)a.counts[b * 4 + 1] + 1e-10f);
-      const float inv_ns = 1.f / ((float)a.counts[b * 4 + 2] + 1e-10f);
+      const float inv_nd = a.fwd_only ? 0.f : 1.f / ((float)a.counts[b * 4 + 0] + 1e-10f);
+      const float inv_no = a.fwd_only ? 0.f : 1.f / ((float)a.counts[b * 4 + 1] + 1e-10f);
+      const float inv_ns = a.fwd_only ? 0.f : 1.f / ((float)a.counts[b * 4 + 2] + 1e-10f);
       const float on_d = misc->on[0] ? 1.f : 0.f, on_c = misc->on[1] ? 1.f : 0.f, on_o = misc->on[2] ? 1.f : 0.f;
       float ls_d = 0.f, ls_c = 0.f, ls_o = 0.f;
       const int np = nr * S;
@@ -496,9 +496,9 @@ k_step_umma(StepParams a, VmbLayout L, const unsigned char* __restrict__ image, 
           const size_t pi = (size_t)(r0n + rl) * S + sidx;
           const float* pp = a.pcs + (size_t)b * a.pcs_stride + pi * 3;
           nx = pp[0]; ny = pp[1]; nz = pp[2];
-          if (hsel == 0) nzv = a.z[(size_t)b * a.z_stride + pi];
+          if (hsel == 0 && !a.fwd_only) nzv = a.z[(size_t)b * a.z_stride + pi];
         }
-        if (hsel == 1 && p < nr && r0n + p < R) {      // ray threads
+        if (hsel == 1 && p < nr && r0n + p < R && !a.fwd_only) {      // ray threads
           const int ray = r0n + p;
           n_gd = a.gt_depth[(size_t)b * a.gt_depth_stride + ray];
           const float* gcp = a.gt_colour + (size_t)b * a.gt_colour_stride + (size_t)ray * 3;
@@ -582,10 +582,17 @@ k_step_umma(StepParams a, VmbLayout L, const unsigned char* __restrict__ image, 
           c0 = fast_sigmoid(v[1] + wf[F_BOC + 0]); c1 = fast_sigmoid(v[2] + wf[F_BOC + 1]); c2 = fast_sigmoid(v[3] + wf[F_BOC + 2]);
           sc[R_OCC * 128 + p] = occ; sc[R_F * 128 + p] = 1.f - occ + 1e-10f;
           sc[R_C0 * 128 + p] = c0; sc[R_C1 * 128 + p] = c1; sc[R_C2 * 128 + p] = c2;
+          if (a.fwd_only && p < np && r0 + rl < R) {     // eval_points (trainer.py:77-90): raw alpha*10, sigmoid colour per point
+            const size_t n = (size_t)(r0 + rl) * S + sidx;
+            a.out_alpha[(size_t)b * a.alpha_stride + n] = (v[0] + wf[F_BA]) * 10.0f;
+            float* oc = a.out_colour + (size_t)b * a.colour_stride + n * 3;
+            oc[0] = c0; oc[1] = c1; oc[2] = c2;
+          }
         }
         TRG();
         group_bar(g);
         TRG();
+        if (a.fwd_only) continue;
         // ---- per-ray: termination weights, rendered depth/colour/opacity, losses, ray gradients
         if (hsel == 1 && p < nr) {
           float gD = 0.f, gC0 = 0.f, gC1 = 0.f, gC2 = 0.f, gO = 0.f;

@@ -230,6 +230,12 @@ int vmb_forward(vmb_handle* h, const vmb_forward_args* a, void* stream) {
   sp.fwd_only = 1;
   sp.out_alpha = a->alpha; sp.alpha_stride = a->alpha_stride;
   sp.out_colour = a->colour; sp.colour_stride = a->colour_stride;
+  if (a->image && h->umma_ok) {
+    std::string err;
+    const int rc = umma_launch_step(h->L, sp, a->image, (cudaStream_t)stream, err);
+    if (rc) return fail(h, rc == -4 ? VMB_E_UNSUPPORTED : VMB_E_CUDA, err);
+    return VMB_OK;
+  }
   return dispatch_fp32(h, sp, (cudaStream_t)stream);
 }
 
