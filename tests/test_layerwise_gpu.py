@@ -89,3 +89,19 @@ def test_layerwise_speed_vs_fp32_kernel_imap_shape():
     print(f"iMAP step 1 x {R} x {S}, H={H}: layerwise {out['layerwise']:.2f} ms ({flop / out['layerwise'] / 1e9:.0f} TFLOP/s), "
           f"fp32 kernel {out['fp32']:.2f} ms")
     assert out["layerwise"] < out["fp32"]
+
+
+@pytest.mark.parametrize("H,N", [(128, 3000), (64, 300001), (256, 1000)])
+def test_eval_points_layerwise_forward_matches_oracle(H, N):
+    """Trainer.eval_points (trainer.py:77-90) on the layer-wise tcgen05 GEMMs; N = 300001 crosses the internal
+    262144-point chunking used to bound the activation workspace for 256^3 grids."""
+    params = vo.init_params(1, H, seed=11)
+    pts = (torch.rand(1, N, 3, generator=torch.Generator().manual_seed(2)) - 0.5) * 8
+    alpha_ref, col_ref = vo.forward(params, torch.full((1,), 5.0), pts.view(1, N, 1, 3))
+    ens = make_ensemble(params, 5.0, H, impl="layerwise")
+    alpha, col = ens.eval_points(pts.cuda())
+    a32, c32 = ens.eval_points(pts.cuda(), impl="fp32")
+    assert rel_l2(a32, alpha_ref.view(1, N)) < 1e-4
+    print(f"H={H} eval_points layer-wise vs oracle: alpha", rel_l2(alpha, alpha_ref.view(1, N)), "colour", rel_l2(col, col_ref.view(1, N, 3)))
+    assert rel_l2(alpha, alpha_ref.view(1, N)) < 3e-3
+    assert rel_l2(col, col_ref.view(1, N, 3)) < 1e-3

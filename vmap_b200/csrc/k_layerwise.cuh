@@ -123,7 +123,8 @@ __global__ void __launch_bounds__(128) k_lw_pe(const float* __restrict__ pcs, co
 template <int H>
 __global__ void __launch_bounds__(128) k_lw_heads(const __half* __restrict__ X4, const __half* __restrict__ XC,
                                                   const float* __restrict__ P, VmbLayout L, long long np,
-                                                  float* __restrict__ occ, float* __restrict__ col) {
+                                                  float* __restrict__ occ, float* __restrict__ col, int raw) {
+  // raw != 0 (eval_points, trainer.py:77-90): occ receives alpha*10 before the sigmoid
   __shared__ float w[4 * H];
   for (int i = threadIdx.x; i < H; i += 128) w[i] = P[L.o_Wa + i];
   for (int i = threadIdx.x; i < 3 * H; i += 128) w[H + i] = P[L.o_Woc + i];
@@ -146,7 +147,7 @@ __global__ void __launch_bounds__(128) k_lw_heads(const __half* __restrict__ X4,
       c0 = fmaf(fc, w[H + o], c0); c1 = fmaf(fc, w[2 * H + o], c1); c2 = fmaf(fc, w[3 * H + o], c2);
     }
   }
-  occ[p] = vmb_sigmoid((a + P[L.o_ba]) * 10.0f);
+  occ[p] = raw ? (a + P[L.o_ba]) * 10.0f : vmb_sigmoid((a + P[L.o_ba]) * 10.0f);
   col[p * 3] = vmb_sigmoid(c0 + P[L.o_boc]); col[p * 3 + 1] = vmb_sigmoid(c1 + P[L.o_boc + 1]);
   col[p * 3 + 2] = vmb_sigmoid(c2 + P[L.o_boc + 2]);
 }
@@ -375,13 +376,14 @@ __global__ void __launch_bounds__(128) k_lw_pe_bwd(const float* __restrict__ pcs
 
 template <int H>
 static int step_object(Workspace& ws, const VmbLayout& L, const StepParams& sp, const __half* image, int b, cudaStream_t st,
-                       std::string& err) {
-  const long long np = (long long)sp.R * sp.S;
+                       std::string& err, long long fwd_p0 = 0, long long fwd_np = 0) {
+  // fwd_only (vmb_forward): points [fwd_p0, fwd_p0 + fwd_np) of object b, raw head outputs, no render
+  const long long np = sp.fwd_only ? fwd_np : (long long)sp.R * sp.S;
   const int mt = (int)((np + BM - 1) / BM);
   const float* Pb = sp.params + (size_t)b * L.stride;
   float* G = sp.grads ? sp.grads + (size_t)b * L.stride : nullptr;
   const __half* Wi = image + (size_t)b * img_halves(H);
-  const float* pcs = sp.pcs + (size_t)b * sp.pcs_stride;
+  const float* pcs = sp.pcs + (size_t)b * sp.pcs_stride + (sp.fwd_only ? fwd_p0 * 3 : 0);
   const float* dirs = Pb + L.o_B;
   const float* scale_p = sp.scale + b;
   const int nblk = (int)((np + 127) / 128);
@@ -401,7 +403,13 @@ static int step_object(Workspace& ws, const VmbLayout& L, const StepParams& sp, 
   LW_TRY(fwd(opX(ws.X2), opE1, H, E1W, off_cat(H), H + 96, L.o_bcat, ws.X3));
   LW_TRY(fwd(opX(ws.X3), none, H, 0, off_m2(H), H, L.o_bm2, ws.X4));
   LW_TRY(fwd(opX(ws.X4), opE2, H, E2W, off_cl(H), H + 48, L.o_bcl, ws.XC));
-  k_lw_heads<H><<<nblk, 128, 0, st>>>(ws.X4, ws.XC, Pb, L, np, ws.occ, ws.col);
+  if (sp.fwd_only) {
+    k_lw_heads<H><<<nblk, 128, 0, st>>>(ws.X4, ws.XC, Pb, L, np, sp.out_alpha + (size_t)b * sp.alpha_stride + fwd_p0,
+                                        sp.out_colour + (size_t)b * sp.colour_stride + fwd_p0 * 3, 1);
+    LW_TRY(cudaGetLastError());
+    return 0;
+  }
+  k_lw_heads<H><<<nblk, 128, 0, st>>>(ws.X4, ws.XC, Pb, L, np, ws.occ, ws.col, 0);
   RenderArgs ra;
   ra.b = b; ra.R = sp.R; ra.S = sp.S; ra.B = sp.B;
   ra.z = sp.z + (size_t)b * sp.z_stride; ra.gt_depth = sp.gt_depth + (size_t)b * sp.gt_depth_stride;
@@ -484,6 +492,27 @@ static int step_object(Workspace& ws, const VmbLayout& L, const StepParams& sp, 
   }
   k_lw_pe_bwd<<<nblk, 128, PEB_SMEM, st>>>(pcs, dirs, scale_p, np, ws.dE, G + L.o_B);
   LW_TRY(cudaGetLastError());
+  return 0;
+}
+
+// forward only (vmb_forward): chunks of FWD_CHUNK points so the activation workspace stays bounded for 256^3 grids
+constexpr long long FWD_CHUNK = 1LL << 18;
+static int launch_forward(Workspace& ws, const VmbLayout& L, const StepParams& sp, const void* image, cudaStream_t st, std::string& err) {
+  if (!get_encode()) { err = "cuTensorMapEncodeTiled not available from the driver"; return -2; }
+  const long long N = sp.R;
+  LW_TRY(ws.ensure(std::min(N, FWD_CHUNK), L.H));
+  for (int b = 0; b < sp.B; ++b)
+    for (long long p0 = 0; p0 < N; p0 += FWD_CHUNK) {
+      const long long n = std::min(FWD_CHUNK, N - p0);
+      int rc;
+      switch (L.H) {
+        case 64:  rc = step_object<64>(ws, L, sp, (const __half*)image, b, st, err, p0, n); break;
+        case 128: rc = step_object<128>(ws, L, sp, (const __half*)image, b, st, err, p0, n); break;
+        case 256: rc = step_object<256>(ws, L, sp, (const __half*)image, b, st, err, p0, n); break;
+        default: err = "layer-wise path: hidden must be 64, 128 or 256"; return -4;
+      }
+      if (rc) return rc;
+    }
   return 0;
 }
 

@@ -236,6 +236,12 @@ int vmb_forward(vmb_handle* h, const vmb_forward_args* a, void* stream) {
     if (rc) return fail(h, rc == -4 ? VMB_E_UNSUPPORTED : VMB_E_CUDA, err);
     return VMB_OK;
   }
+  if (a->image && h->lw_ok) {
+    std::string err;
+    const int rc = lw::launch_forward(h->ws, h->L, sp, a->image, (cudaStream_t)stream, err);
+    if (rc) return fail(h, rc == -4 ? VMB_E_UNSUPPORTED : VMB_E_CUDA, err);
+    return VMB_OK;
+  }
   return dispatch_fp32(h, sp, (cudaStream_t)stream);
 }
 

@@ -210,7 +210,7 @@ class VmapEnsemble:
     def eval_points(self, points: torch.Tensor, impl: Optional[str] = None):
         """Forward only on raw points [B,N,3] -> alpha [B,N], colour [B,N,3] (trainer.py:77-90).
         ``impl="fp32"`` forces the CUDA-core kernel; otherwise hidden 32 runs the forward half of the fused
-        tcgen05 kernel on the fp16 weight image."""
+        tcgen05 kernel and hidden 64/128/256 the layer-wise tcgen05 GEMMs, on the fp16 weight image."""
         B, N, _ = points.shape
         assert B == self.n_obj and points.is_contiguous() and points.dtype == torch.float32
         alpha = torch.empty(B, N, dtype=torch.float32, device=self.device)
@@ -221,7 +221,7 @@ class VmapEnsemble:
         a.params, a.scale = _ptr(self.params), _ptr(self.scale)
         a.alpha, a.alpha_stride = _ptr(alpha), N
         a.colour, a.colour_stride = _ptr(colour), N * 3
-        if (impl or self.impl) != "fp32" and self.hidden == 32 and self.image is not None:
+        if (impl or self.impl) != "fp32" and self.image is not None:
             a.image = _ptr(self.image)
         with torch.cuda.device(self.device):
             _lib.check(self._handle, self.lib.vmb_forward(self._handle, C.byref(a), _stream()), "vmb_forward")
