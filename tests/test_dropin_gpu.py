@@ -128,8 +128,12 @@ def test_train_loop_dropin_matches_oracle(tmp_path):
     assert occ.shape == (500,) and colour.shape == (500, 3) and bool(((occ >= 0) & (occ <= 1)).all())
 
 
-def test_separate_background_model_path():
-    """do_bg: a non-vmapped H=128 model trained beside the stack (train.py:308-316)."""
+@pytest.mark.parametrize("impl", ["fp32", "auto"])
+def test_separate_background_model_path(impl, monkeypatch):
+    """do_bg: a non-vmapped H=128 model trained beside the stack (train.py:308-316).  "auto" resolves to the layer-wise
+    tensor-core path (fp16 operands) for hidden 128; VMB_IMPL=fp32 pins the CUDA-core parity kernel."""
+    monkeypatch.setenv("VMB_IMPL", impl)
+    tol_loss, tol_par = (1e-4, 1e-4) if impl == "fp32" else (3e-3, 2e-2)
     import vmap_b200.loss as loss
     from vmap_b200.embedding import UniDirsEmbed
     from vmap_b200.model import OccupancyMap, init_weights
@@ -151,6 +155,6 @@ def test_separate_background_model_path():
                                           b["gt_colour"].cuda(), b["sem"].cuda(), b["mask_depth"].cuda(), b["z"].cuda())
         bg_loss.backward(); opt.step(); opt.zero_grad(set_to_none=True)
         ref = float(orc.step(b))
-        assert abs(float(bg_loss) - ref) < 1e-4 * abs(ref)
+        assert abs(float(bg_loss) - ref) < tol_loss * abs(ref)
     for k, p in fc.named_parameters():
-        assert rel_l2(p, orc.params[k][0]) < 1e-4, k
+        assert rel_l2(p, orc.params[k][0]) < tol_par, k

@@ -10,6 +10,7 @@ what ``utils.update_vmap`` + ``torch.optim.AdamW`` hold in the reference
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Dict, Optional
 
 import torch
@@ -43,7 +44,8 @@ class VmapEnsemble:
         self.n_obj, self.hidden, self.n_unidir_funcs = n_obj, hidden, n_unidir_funcs
         self.n_freq = n_unidir_funcs + 1
         self.lr, self.weight_decay, self.betas, self.eps = lr, weight_decay, betas, eps
-        self.impl = impl
+        # VMB_IMPL=fp32|umma|layerwise overrides the default choice ("auto"), e.g. to run the drop-in on the fp32 parity kernel
+        self.impl = os.environ.get("VMB_IMPL", impl) if impl == "auto" else impl
         self.colour_scaling, self.opacity_scaling = colour_scaling, opacity_scaling
         self.count, self.stride, self.offsets, self.sizes = _lib.param_layout(hidden, self.n_freq)
         assert (self.count, self.stride, self.offsets, self.sizes) == host_offsets(hidden, n_unidir_funcs)
