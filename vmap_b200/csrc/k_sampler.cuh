@@ -2,8 +2,10 @@
 // Restates sceneObject.get_training_samples + sample_3d_points + stratified_bins +
 // normal_bins_sampling + origin_dirs_W (vmap.py:319-364, 366-459, 45-72, 75-87, 31-41)
 // per ray instead of per compacted group, and folds in the stack + /255 of
-// train.py:255-260.  No host syncs: the data-dependent max_bound (vmap.py:397) is a
-// block reduction (one CTA per object), the group branches are per-ray selects.
+// train.py:255-260.  No host syncs: the data-dependent max_bound (vmap.py:397) is reduced on
+// the device (block reduction + one atomicMax per CTA on an order-preserving key) between the
+// two passes, the group branches are per-ray selects.  Both passes run on a (ray chunks x objects)
+// grid, so a frame's sampling fills the GPU even with a handful of objects.
 //
 // Index / bin arithmetic uses explicit round-to-nearest mul/add (no FMA contraction) so
 // that with injected randoms the integer outputs and z are bit-identical to torch's
@@ -91,17 +93,24 @@ __device__ __forceinline__ float strat(float lo, float hi, const float* lim, int
   return __fadd_rn(lower, __fmul_rn(u, __fdiv_rn(rng, (float)n)));
 }
 
-__global__ void __launch_bounds__(512) k_sample(SampleParams a) {
-  const int b = blockIdx.x;
-  const int N = a.n_frames * a.n_pix;
-  const int S = a.n1 + a.n2;
-  __shared__ float s_max[16];
-  __shared__ float s_maxb;
-  const size_t pix_per_kf = (size_t)a.W * a.Hh;
+// order-preserving float <-> uint32 key (atomicMax on the key == max on the float)
+__device__ __forceinline__ unsigned int fkey(float f) {
+  const unsigned int u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float fkey_inv(unsigned int k) {
+  return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
 
-  // pass 1: gather pixels, write the 2-D targets, reduce max depth (vmap.py:353-354,397)
+// Pass 1 (grid = ray chunks x objects): gather pixels, write the 2-D targets, reduce the object's max sampled depth
+// (vmap.py:353-354,397) into smax[b] (zeroed by the host before the launch; key 0 is below every float's key).
+__global__ void __launch_bounds__(256) k_sample_gather(SampleParams a, unsigned int* __restrict__ smax) {
+  const int b = blockIdx.y;
+  const int N = a.n_frames * a.n_pix;
+  __shared__ float s_max[8];
+  const size_t pix_per_kf = (size_t)a.W * a.Hh;
   float mx = -3.0e38f;
-  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
     const RayPick r = pick_pixel(a, b, i);
     uchar4 px;
     float d;
@@ -133,15 +142,27 @@ __global__ void __launch_bounds__(512) k_sample(SampleParams a) {
   if (threadIdx.x == 0) {
     float m = s_max[0];
     for (int w = 1; w < (int)(blockDim.x >> 5); ++w) m = fmaxf(m, s_max[w]);
-    s_maxb = m;
+    atomicMax(smax + b, fkey(m));
   }
-  __syncthreads();
-  const float max_bound = s_maxb;
+}
 
-  // pass 2: per-ray sample depths and 3-D points (vmap.py:366-459)
+// Pass 2 (grid = ray chunks x objects): per-ray sample depths and 3-D points (vmap.py:366-459)
+__global__ void __launch_bounds__(256) k_sample_points(SampleParams a, const unsigned int* __restrict__ smax) {
+  const int b = blockIdx.y;
+  const int N = a.n_frames * a.n_pix;
+  const int S = a.n1 + a.n2;
+  const float max_bound = fkey_inv(smax[b]);
+  // a thread owns a ray (S x 16 B of output), so direct stores would touch 32 lines per instruction: the block's
+  // rays are consecutive in memory, results are staged in shared memory and written out as one coalesced span
+  extern __shared__ float s_out[];                 // [256][S] z | [256][S][3] points
+  float* s_z = s_out;
+  float* s_p = s_out + 256 * S;
+
   const float* limS = a.lim, * lim1 = a.lim + 33, * lim2 = a.lim + 66;
   const uint32_t k0 = (uint32_t)a.seed, k1 = (uint32_t)(a.seed >> 32);
-  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+  for (int base = blockIdx.x * 256; base < N; base += gridDim.x * 256) {
+    const int i = base + threadIdx.x;
+    if (i < N) {
     const RayPick r = pick_pixel(a, b, i);
     const size_t o = (size_t)b * N + i;
     const float d = a.gt_depth[o];
@@ -203,11 +224,19 @@ __global__ void __launch_bounds__(512) k_sample(SampleParams a) {
       } else {
         zz = strat(__fsub_rn(d, a.eps), __fadd_rn(d, a.oeps), lim2, a.n2, s - a.n1, uz[s]);   // vmap.py:447-450
       }
-      a.z[o * S + s] = zz;
-      float* pc = a.pcs + (o * S + s) * 3;                                     // vmap.py:455
+      s_z[threadIdx.x * S + s] = zz;
+      float* pc = s_p + (threadIdx.x * S + s) * 3;                             // vmap.py:455
       pc[0] = __fadd_rn(o0, __fmul_rn(dw0, zz));
       pc[1] = __fadd_rn(o1, __fmul_rn(dw1, zz));
       pc[2] = __fadd_rn(o2, __fmul_rn(dw2, zz));
     }
+    }
+    __syncthreads();
+    const int nv = min(256, N - base);
+    float* gz = a.z + ((size_t)b * N + base) * S;
+    for (int k = threadIdx.x; k < nv * S; k += 256) gz[k] = s_z[k];
+    float* gp = a.pcs + ((size_t)b * N + base) * S * 3;
+    for (int k = threadIdx.x; k < nv * S * 3; k += 256) gp[k] = s_p[k];
+    __syncthreads();
   }
 }

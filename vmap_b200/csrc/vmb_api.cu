@@ -23,6 +23,7 @@ struct vmb_handle {
   int* d_counts;          // [max_obj][4]
   int* d_img_index;       // [P] param index -> half index inside the fp16 image (or -1)
   unsigned int* d_ticket; // last-block ticket of the fused AdamW (device step counter mode)
+  unsigned int* d_smax;   // [max_obj] sampler: per-object max sampled depth (order-preserving key)
   int img_halves;
   bool umma_ok;           // hidden 32: fused tcgen05 kernel + its pre-swizzled fp16 image
   bool lw_ok;             // hidden 64/128/256: layer-wise tcgen05 GEMM path + row-major fp16 image
@@ -115,10 +116,11 @@ int vmb_create(vmb_handle** out, int device, int max_obj, int hidden, int n_freq
   h->n_sm = 148;
   cudaDeviceGetAttribute(&h->n_sm, cudaDevAttrMultiProcessorCount, device);
   h->L = vmb_make_layout(hidden, n_freq);
-  h->d_counts = nullptr; h->d_img_index = nullptr; h->d_ticket = nullptr; h->img_halves = 0; h->umma_ok = false; h->lw_ok = false;
+  h->d_counts = nullptr; h->d_img_index = nullptr; h->d_ticket = nullptr; h->d_smax = nullptr; h->img_halves = 0; h->umma_ok = false; h->lw_ok = false;
   cudaError_t e = cudaMalloc(&h->d_counts, sizeof(int) * 4 * max_obj);
   if (e == cudaSuccess) e = cudaMalloc(&h->d_ticket, sizeof(unsigned int));
   if (e == cudaSuccess) e = cudaMemset(h->d_ticket, 0, sizeof(unsigned int));
+  if (e == cudaSuccess) e = cudaMalloc(&h->d_smax, sizeof(unsigned int) * (size_t)max_obj);
   if (e != cudaSuccess) { delete h; return fail(nullptr, VMB_E_NOMEM, cudaGetErrorString(e)); }
   if (hidden == 32 && n_freq == 6) {
     std::vector<int> idx(h->L.P);
@@ -147,6 +149,7 @@ void vmb_destroy(vmb_handle* h) {
   if (h->d_counts) cudaFree(h->d_counts);
   if (h->d_img_index) cudaFree(h->d_img_index);
   if (h->d_ticket) cudaFree(h->d_ticket);
+  if (h->d_smax) cudaFree(h->d_smax);
   h->ws.release();
   delete h;
 }
@@ -314,7 +317,23 @@ int vmb_sample(vmb_handle* h, const vmb_sample_args* a, void* stream) {
   p.sem = a->sem; p.mask = a->mask_depth;
   p.st_rgbx = reinterpret_cast<const uchar4*>(a->store_rgbx); p.st_depth = a->store_depth; p.st_inst = a->store_inst;
   p.st_twc = a->store_t_wc; p.kf_slot = a->kf_slot; p.bbox_flat = a->kf_bbox; p.obj_id = a->obj_id; p.kf_stride = a->kf_stride;
-  k_sample<<<a->n_obj, 512, 0, (cudaStream_t)stream>>>(p);
+  if (a->n_obj > h->max_obj) return fail(h, VMB_E_ARG, "vmb_sample: n_obj exceeds the handle's max_obj");
+  const int N = a->n_frames * a->n_pix;
+  // enough CTAs to fill the GPU a few times over, never more than one ray per thread needs
+  int chunks = (N + 255) / 256;
+  const int want = (8 * h->n_sm + a->n_obj - 1) / a->n_obj;
+  if (chunks > want) chunks = want;
+  if (chunks < 1) chunks = 1;
+  cudaStream_t st = (cudaStream_t)stream;
+  CUDA_TRY(h, cudaMemsetAsync(h->d_smax, 0, sizeof(unsigned int) * a->n_obj, st));
+  k_sample_gather<<<dim3(chunks, a->n_obj), 256, 0, st>>>(p, h->d_smax);
+  const int smem_pts = 256 * (a->n_bins_cam2surface + a->n_bins) * 16;      // staged z + points of 256 rays
+  static bool attr_set[64] = {};
+  if (!attr_set[h->device & 63]) {
+    CUDA_TRY(h, cudaFuncSetAttribute(k_sample_points, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 32 * 16));
+    attr_set[h->device & 63] = true;
+  }
+  k_sample_points<<<dim3(chunks, a->n_obj), 256, smem_pts, st>>>(p, h->d_smax);
   CUDA_TRY(h, cudaGetLastError());
   return VMB_OK;
 }

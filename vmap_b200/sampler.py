@@ -105,15 +105,24 @@ class BatchedSampler:
             assert o.t_wc_batch.is_contiguous() and o.bbox.is_contiguous()
             assert o.rgbs_batch.dtype == torch.uint8 and o.depth_batch.dtype == torch.float32
             assert o.rgbs_batch.device == dev
-        ptrs = torch.tensor([[o.rgbs_batch.data_ptr(), o.depth_batch.data_ptr(), o.t_wc_batch.data_ptr(),
-                              o.bbox.data_ptr()] for o in objects], dtype=torch.int64).t().contiguous().to(dev)
-        nkf = torch.tensor([o.n_keyframes for o in objects], dtype=torch.int32, device=dev)
-        latest = torch.tensor([_latest2(o.latest_kf) for o in objects], dtype=torch.int32, device=dev)
+        # one pinned staging buffer -> ONE small host->device copy: [4][B] pointers | [B] n_kf + [B][2] latest (int32 pairs)
+        i32 = [o.n_keyframes for o in objects] + [v for o in objects for v in _latest2(o.latest_kf)]
+        if len(i32) & 1:
+            i32.append(0)
+        cols = ([o.rgbs_batch.data_ptr() for o in objects] + [o.depth_batch.data_ptr() for o in objects] +
+                [o.t_wc_batch.data_ptr() for o in objects] + [o.bbox.data_ptr() for o in objects])
+        host = torch.tensor(cols + [(i32[k] & 0xffffffff) | (i32[k + 1] << 32) for k in range(0, len(i32), 2)],
+                            dtype=torch.int64)
+        host = host.pin_memory()
+        devbuf = host.to(dev, non_blocking=True)
+        ptrs = devbuf[:4 * B].view(4, B)
+        tail_d = devbuf[4 * B:].view(torch.int32)
+        nkf, latest = tail_d[:B], tail_d[B:3 * B]
         out = self._outputs(B, N, S, want_u8)
         a = _lib.SampleArgs()
         a.rgbs, a.depths, a.t_wc, a.bbox = _p(ptrs[0]), _p(ptrs[1]), _p(ptrs[2]), _p(ptrs[3])
         a.n_keyframes, a.latest_kf = _p(nkf), _p(latest)
-        return self._launch(a, out, B, n_frames, n_pix, W, H, rays_dir, seed, offset, inject, (ptrs, nkf, latest))
+        return self._launch(a, out, B, n_frames, n_pix, W, H, rays_dir, seed, offset, inject, (host, devbuf))
 
     def sample_store(self, store, tables: "KeyframeTables", n_frames: int, n_pix: int, rays_dir: torch.Tensor,
                      seed: int = 0, offset: int = 0, inject: Optional[Dict[str, torch.Tensor]] = None,
