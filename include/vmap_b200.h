@@ -206,6 +206,9 @@ typedef struct vmb_sample_args {
   const float* kf_bbox;             /* [B][kf_stride][4] u_lo,u_hi,v_lo,v_hi                       */
   const int* obj_id;                /* [B] instance id of each object                              */
   int kf_stride;
+  /* Optional device-resident draw counter: when set it replaces `offset`, so a captured CUDA graph of a whole
+   * frame (sampler + its optimisation steps) draws fresh samples on every replay (the caller increments it). */
+  const unsigned long long* offset_dev;
 } vmb_sample_args;
 
 int vmb_sample(vmb_handle* h, const vmb_sample_args* a, void* stream);

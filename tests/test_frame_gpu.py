@@ -1,0 +1,74 @@
+"""GPU: one mapping frame (sampler + its optimisation steps) as a captured CUDA graph == the eager loop."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import sampler_oracle as so
+from tests._util import rel_l2
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _objects(B, KF, W, H, seed):
+    from vmap_b200.sampler import KeyframeSet
+    g = torch.Generator().manual_seed(seed)
+    sets = []
+    for b in range(B):
+        rgbs = torch.randint(0, 256, (KF, W, H, 4), generator=g, dtype=torch.uint8)
+        rgbs[..., 3] = (torch.rand(KF, W, H, generator=g) * 3).to(torch.uint8).clamp(0, 2)
+        depth = torch.rand(KF, W, H, generator=g) * 3 + 0.5
+        depth[torch.rand(KF, W, H, generator=g) < 0.1] = 0
+        twc = torch.eye(4).repeat(KF, 1, 1); twc[:, :3, 3] = torch.rand(KF, 3, generator=g) - 0.5
+        bbox = torch.tensor([[2.0, W - 3.0, 2.0, H - 3.0]]).repeat(KF, 1)
+        sets.append(KeyframeSet(rgbs.to(DEV), depth.to(DEV), twc.to(DEV), bbox.to(DEV), KF, [KF - 2, KF - 1]))
+    return sets
+
+
+@pytest.mark.parametrize("use_store", [False, True])
+def test_frame_graph_matches_eager_loop(use_store):
+    from vmap_b200 import synth
+    from vmap_b200.ensemble import VmapEnsemble
+    from vmap_b200.frame import FrameLoop
+    from vmap_b200.sampler import BatchedSampler, KeyframeTables
+    B, KF, W, H, n_frames, n_pix, n_iter = 3, 4, 64, 48, 8, 15, 4
+    rays = so.camera_ray_dirs(W, H, 60.0, 60.0, W / 2 - 0.5, H / 2 - 0.5).to(DEV)
+    store = kt = sets = None
+    if use_store:
+        from vmap_b200.keyframes import FrameStore
+        store = FrameStore(W, H, 8, DEV, max_id=64)
+        rng = np.random.default_rng(0)
+        for f in range(KF):
+            inst = torch.from_numpy(rng.integers(-1, 4, (W, H)).astype(np.int32))
+            store.put(torch.from_numpy(rng.integers(0, 255, (W, H, 3), dtype=np.uint8)),
+                      torch.from_numpy((rng.random((W, H), dtype=np.float32) * 3 + 0.5)), inst, torch.eye(4), frame_id=f)
+        kt = KeyframeTables(np.tile(np.arange(KF, dtype=np.int32), (B, 1)),
+                            np.tile(np.array([2.0, W - 3.0, 2.0, H - 3.0], dtype=np.float32), (B, KF, 1)),
+                            [1, 2, 3], [KF] * B, [[KF - 2, KF - 1]] * B)
+    else:
+        sets = _objects(B, KF, W, H, seed=1)
+    params = synth.init_params(B, 32, seed=0)
+    results = []
+    for mode in ("eager", "graph"):
+        ens = VmapEnsemble(B, hidden=32, scale=2.0, device=DEV)
+        ens.load_stacked(params)
+        fl = FrameLoop(ens, BatchedSampler(DEV, 1, 9), n_frames, n_pix, n_iter, rays, store=store,
+                       kf_stride=KF if use_store else 0, seed=5, first_offset=7)
+        if use_store:
+            fl.set_store_tables(kt)
+        else:
+            fl.set_objects(sets)
+        losses, draws = [], []
+        for frame in range(3):
+            l = fl.run_eager() if mode == "eager" else fl.run()
+            losses.append(l.clone()); draws.append(fl.out["pcs"].clone())
+        torch.cuda.synchronize()
+        ens.check_status()
+        assert int(fl.counter) == 7 + 3 and ens.step_count == 3 * n_iter and int(ens.step_counter) == 3 * n_iter
+        results.append((torch.stack(losses).cpu(), draws, ens.params.clone()))
+    (l_e, d_e, p_e), (l_g, d_g, p_g) = results
+    for a, b in zip(d_e, d_g):
+        assert torch.equal(a, b)                       # same draws frame by frame (device draw counter)
+    assert not torch.equal(d_g[0], d_g[1])             # and fresh ones every frame
+    assert torch.allclose(l_e, l_g, rtol=2e-3, atol=1e-4), (l_e, l_g)
+    assert rel_l2(p_g, p_e) < 2e-3                     # only the atomics' summation order differs

@@ -48,7 +48,24 @@ for name, n_frames, n_pix, n_iter in (("shipped_120rays", 100, 24, 20), ("baseli
         t_s += e[0].elapsed_time(e[1]); t_t += e[1].elapsed_time(e[2])
     out[name] = {"objects": B, "rays_per_object_per_frame": n_frames * n_pix, "sampler_ms": t_s / n, "train_20_steps_ms": t_t / n,
                  "sampler_Mrays_per_s": B * n_frames * n_pix / (t_s / n) / 1e3, "frame_ms": (t_s + t_t) / n}
-ens.check_status()
+# the same frame as ONE captured CUDA graph (vmap_b200/frame.py)
+from vmap_b200.frame import FrameLoop
+for name, n_frames, n_pix, n_iter in (("shipped_120rays", 100, 24, 20), ("baseline_1200rays", 1000, 24, 20)):
+    ens2 = VmapEnsemble(B, hidden=32, scale=2.0, device=dev)        # fresh weights: random targets diverge after ~1000 steps
+    ens2.load_stacked(vo.init_params(B, 32, seed=0))
+    fl = FrameLoop(ens2, smp, n_frames, n_pix, n_iter, rays, seed=3)
+    fl.set_objects(objs)
+    fl.capture()
+    for _ in range(3): fl.run()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10):
+        fl.set_objects(objs)          # per-frame host work: refill the pinned tables
+        fl.run()
+    e1.record(); torch.cuda.synchronize()
+    out[name]["frame_graph_ms"] = e0.elapsed_time(e1) / 10
+    ens2.check_status()
 # CPU sampler baseline: oracle restatement of vmap.py:319-459 for ONE object (the reference loops over objects)
 torch.set_num_threads(16)
 o0 = objs[0]

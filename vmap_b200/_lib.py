@@ -76,6 +76,7 @@ class SampleArgs(C.Structure):
         ("sem", _vp), ("mask_depth", _vp),
         ("store_rgbx", _vp), ("store_depth", _vp), ("store_inst", _vp), ("store_t_wc", _vp),
         ("kf_slot", _vp), ("kf_bbox", _vp), ("obj_id", _vp), ("kf_stride", C.c_int),
+        ("offset_dev", _vp),
     ]
 
 

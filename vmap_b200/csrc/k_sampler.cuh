@@ -33,7 +33,12 @@ struct SampleParams {
   // state is derived from the instance image (train.py:126-128: this object -> 1, id -1 -> 2, else 0)
   const uchar4* st_rgbx; const float* st_depth; const int* st_inst; const float* st_twc;
   const int* kf_slot; const float* bbox_flat; const int* obj_id; int kf_stride;
+  const unsigned long long* offset_dev;   // optional device-resident draw counter (CUDA-graph replay of a frame)
 };
+
+__device__ __forceinline__ uint32_t sample_offset(const SampleParams& a) {
+  return (uint32_t)(a.offset_dev ? *a.offset_dev : a.offset);
+}
 
 __device__ __forceinline__ const float* sample_bbox(const SampleParams& a, int b, int kf) {
   return a.st_rgbx ? a.bbox_flat + ((size_t)b * a.kf_stride + kf) * 4 : a.bbox[b] + kf * 4;
@@ -66,7 +71,7 @@ __device__ __forceinline__ RayPick pick_pixel(const SampleParams& a, int b, int 
     r.kf = a.latest[b * 2 + (f - (a.n_frames - 2))];
   } else {
     uint32_t o[4];
-    philox4x32_10((uint32_t)f, 0u, (uint32_t)b, (uint32_t)a.offset, k0, k1, o);
+    philox4x32_10((uint32_t)f, 0u, (uint32_t)b, sample_offset(a), k0, k1, o);
     r.kf = min((int)(u01(o[0]) * (float)nkf), nkf - 1);
   }
   float uw, uh;
@@ -75,7 +80,7 @@ __device__ __forceinline__ RayPick pick_pixel(const SampleParams& a, int b, int 
     uh = a.inj_u_h[(size_t)b * a.n_frames * a.n_pix + i];
   } else {
     uint32_t o[4];
-    philox4x32_10((uint32_t)i, 1u, (uint32_t)b, (uint32_t)a.offset, k0, k1, o);
+    philox4x32_10((uint32_t)i, 1u, (uint32_t)b, sample_offset(a), k0, k1, o);
     uw = u01(o[0]); uh = u01(o[1]);
   }
   const float* bb = sample_bbox(a, b, r.kf);                       // vmap.py:346-351
@@ -176,7 +181,7 @@ __global__ void __launch_bounds__(256) k_sample_points(SampleParams a, const uns
     } else {
       for (int c = 0; c * 4 < S; ++c) {
         uint32_t q[4];
-        philox4x32_10((uint32_t)i * 8u + c, 2u, (uint32_t)b, (uint32_t)a.offset, k0, k1, q);
+        philox4x32_10((uint32_t)i * 8u + c, 2u, (uint32_t)b, sample_offset(a), k0, k1, q);
         for (int j = 0; j < 4 && c * 4 + j < S; ++j) uz[c * 4 + j] = u01(q[j]);
       }
     }
@@ -187,7 +192,7 @@ __global__ void __launch_bounds__(256) k_sample_points(SampleParams a, const uns
         const float sd = a.eps / 3.0f;                            // vmap.py:432 delta/3
         for (int c = 0; c * 4 < a.n2; ++c) {
           uint32_t q[4];
-          philox4x32_10((uint32_t)i * 8u + c, 3u, (uint32_t)b, (uint32_t)a.offset, k0, k1, q);
+          philox4x32_10((uint32_t)i * 8u + c, 3u, (uint32_t)b, sample_offset(a), k0, k1, q);
           const float r0 = sqrtf(-2.f * logf(1.f - u01(q[0]))), r1 = sqrtf(-2.f * logf(1.f - u01(q[2])));
           float s0, c0, s1, c1;
           sincospif(2.f * u01(q[1]), &s0, &c0);

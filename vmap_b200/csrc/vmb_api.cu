@@ -316,6 +316,7 @@ int vmb_sample(vmb_handle* h, const vmb_sample_args* a, void* stream) {
   p.pcs = a->pcs; p.z = a->z_vals; p.gt_depth = a->gt_depth; p.gt_colour = a->gt_colour; p.rgb_u8 = a->gt_rgb_u8;
   p.sem = a->sem; p.mask = a->mask_depth;
   p.st_rgbx = reinterpret_cast<const uchar4*>(a->store_rgbx); p.st_depth = a->store_depth; p.st_inst = a->store_inst;
+  p.offset_dev = a->offset_dev;
   p.st_twc = a->store_t_wc; p.kf_slot = a->kf_slot; p.bbox_flat = a->kf_bbox; p.obj_id = a->obj_id; p.kf_stride = a->kf_stride;
   if (a->n_obj > h->max_obj) return fail(h, VMB_E_ARG, "vmb_sample: n_obj exceeds the handle's max_obj");
   const int N = a->n_frames * a->n_pix;

@@ -1,0 +1,97 @@
+"""One mapping frame as ONE CUDA graph: batched sampler (K3) + the frame's optimisation steps (K0+K1+K2 each).
+
+The reference's per-frame loop (train.py:195-326) is launch-bound at its shipped configuration (20 objects x 120
+rays per step: ~25 us of kernel work per step behind ~60 us of Python + launches).  ``FrameLoop`` captures
+
+    table upload (one small H2D from a pinned buffer) -> K3 pass 1 -> K3 pass 2 -> draw counter += 1
+      -> n_iter x [ K0 mask counts -> K1 fused step on the it-th ray slice -> K2 AdamW -> loss copy ]
+
+once, on persistent buffers, and replays it per frame.  What changes between frames lives in device memory (Adam
+step counter, sampler draw counter) or in the pinned table buffer (keyframe slots / boxes / counts), so a replay
+draws fresh samples and continues the optimiser exactly as the eager loop would.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence
+
+import torch
+
+from .ensemble import VmapEnsemble
+from .sampler import BatchedSampler, KeyframeSet, KeyframeTables, SamplerTables
+
+
+class FrameLoop:
+    def __init__(self, ens: VmapEnsemble, sampler: BatchedSampler, n_frames: int, n_pix: int, n_iter: int,
+                 rays_dir: torch.Tensor, store=None, kf_stride: int = 0, seed: int = 0, first_offset: int = 0):
+        """``n_frames * n_pix`` rays are drawn per object per frame and consumed in ``n_iter`` slices
+        (train.py:198,270-277).  ``store``/``kf_stride``: shared keyframe store mode (keyframes.FrameStore)."""
+        assert (n_frames * n_pix) % n_iter == 0, "rays per frame must split evenly over the iterations"
+        self.ens, self.smp, self.store = ens, sampler, store
+        self.n_frames, self.n_pix, self.n_iter = n_frames, n_pix, n_iter
+        self.rays_dir = rays_dir.contiguous()
+        self.seed = seed
+        dev = ens.device
+        B = ens.n_obj
+        self.tables = SamplerTables(dev, B, kf_stride=kf_stride if store is not None else 0)
+        self.out = sampler._outputs(B, n_frames * n_pix, sampler.n1 + sampler.n2, False)
+        self.counter = torch.full((1,), first_offset, dtype=torch.int64, device=dev)     # sampler draw counter
+        self.losses = torch.zeros(n_iter, dtype=torch.float32, device=dev)
+        self.graph: Optional[torch.cuda.CUDAGraph] = None
+        self._size_from: Optional[List[KeyframeSet]] = None
+
+    # ---- per-frame host work: only the small tables ------------------------------------------------------
+    def set_objects(self, sets: Sequence[KeyframeSet]) -> None:
+        self.tables.fill_objects(sets)
+        self._size_from = list(sets)[:1]
+
+    def set_store_tables(self, kt: KeyframeTables) -> None:
+        self.tables.fill_store(kt)
+
+    # ---- the frame -----------------------------------------------------------------------------------------
+    def _enqueue(self) -> None:
+        s, R = self.smp, self.n_frames * self.n_pix // self.n_iter
+        self.tables.upload()
+        if self.store is not None:
+            s.sample_store(self.store, self.tables, self.n_frames, self.n_pix, self.rays_dir, seed=self.seed,
+                           out=self.out, offset_dev=self.counter)
+        else:
+            s.sample(self._size_from, self.n_frames, self.n_pix, self.rays_dir, seed=self.seed,
+                     tables=self.tables, out=self.out, offset_dev=self.counter)
+        self.counter += 1
+        for it in range(self.n_iter):
+            self.losses[it] = self.ens.step({k: v[:, it * R:(it + 1) * R] for k, v in self.out.items()})
+
+    def run_eager(self) -> torch.Tensor:
+        """The same frame without a graph (reference for tests / first frames)."""
+        self._enqueue()
+        return self.losses
+
+    def capture(self) -> None:
+        """Warm up once (kernel attributes, allocator) on a side stream, then capture.  The warm-up frame and the
+        capture itself do not advance the optimiser or the draw counter."""
+        ens = self.ens
+        snap = [t.clone() for t in (ens.params, ens.grads, ens.exp_avg, ens.exp_avg_sq, ens.step_counter, self.counter)]
+        img = ens.image.clone() if ens.image is not None else None
+        count = ens.step_count
+        st = torch.cuda.Stream(device=ens.device)
+        st.wait_stream(torch.cuda.current_stream(ens.device))
+        with torch.cuda.stream(st):
+            self._enqueue()
+        torch.cuda.current_stream(ens.device).wait_stream(st)
+        torch.cuda.synchronize(ens.device)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self._enqueue()
+        for dst, src in zip((ens.params, ens.grads, ens.exp_avg, ens.exp_avg_sq, ens.step_counter, self.counter), snap):
+            dst.copy_(src)
+        if img is not None:
+            ens.image.copy_(img)
+        ens.step_count = count
+
+    def run(self) -> torch.Tensor:
+        """Replay the captured frame; returns the per-iteration summed losses (device tensor [n_iter])."""
+        if self.graph is None:
+            self.capture()
+        self.graph.replay()
+        self.ens.step_count += self.n_iter
+        return self.losses

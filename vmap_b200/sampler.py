@@ -71,13 +71,14 @@ class BatchedSampler:
             out["gt_rgb_u8"] = torch.empty(B, N, 3, dtype=torch.uint8, device=dev)
         return out
 
-    def _launch(self, a, out, B, n_frames, n_pix, W, H, rays_dir, seed, offset, inject, keep):
+    def _launch(self, a, out, B, n_frames, n_pix, W, H, rays_dir, seed, offset, inject, keep, offset_dev=None):
         dev = self.device
         a.n_obj, a.n_frames, a.n_pix = B, n_frames, n_pix
         a.n_bins_cam2surface, a.n_bins, a.width, a.height = self.n1, self.n2, W, H
         a.min_bound, a.surface_eps, a.stop_eps = self.min_bound, self.eps, self.oeps
         a.rays_dir, a.bin_limits = _p(rays_dir), _p(self.bin_limits)
         a.seed, a.offset = seed, offset
+        a.offset_dev = _p(offset_dev)
         inj = None
         if inject is not None:
             inj = {k: v.to(dev).contiguous() for k, v in inject.items()}
@@ -94,52 +95,105 @@ class BatchedSampler:
 
     def sample(self, objects: List[KeyframeSet], n_frames: int, n_pix: int, rays_dir: torch.Tensor,
                seed: int = 0, offset: int = 0, inject: Optional[Dict[str, torch.Tensor]] = None,
-               want_u8: bool = False) -> Dict[str, torch.Tensor]:
-        """Per-object keyframe buffers (the reference's layout, vmap.py:137-176)."""
+               want_u8: bool = False, tables: Optional["SamplerTables"] = None, out=None, offset_dev=None
+               ) -> Dict[str, torch.Tensor]:
+        """Per-object keyframe buffers (the reference's layout, vmap.py:137-176).
+        ``tables`` / ``out`` / ``offset_dev``: persistent table + output buffers and a device draw counter, for
+        CUDA-graph capture of a whole frame (frame.FrameLoop); with ``tables`` the caller has already filled and
+        uploaded them and ``objects`` only provides the image size."""
         dev = self.device
         B = len(objects)
         N, S = n_frames * n_pix, self.n1 + self.n2
         W, H = objects[0].rgbs_batch.shape[1], objects[0].rgbs_batch.shape[2]
-        for o in objects:
+        if tables is None:
+            tables = SamplerTables(dev, B)
+            tables.fill_objects(objects)
+            tables.upload()
+        out = out if out is not None else self._outputs(B, N, S, want_u8)
+        a = _lib.SampleArgs()
+        tables.bind(a)
+        return self._launch(a, out, B, n_frames, n_pix, W, H, rays_dir, seed, offset, inject, tables, offset_dev)
+
+    def sample_store(self, store, tables, n_frames: int, n_pix: int, rays_dir: torch.Tensor,
+                     seed: int = 0, offset: int = 0, inject: Optional[Dict[str, torch.Tensor]] = None,
+                     want_u8: bool = False, out=None, offset_dev=None) -> Dict[str, torch.Tensor]:
+        """Shared keyframe store (keyframes.FrameStore): frames stored once, per-object (slot, bbox) tables,
+        pixel state derived from the instance image.  Same draws / outputs as ``sample`` on per-object copies.
+        ``tables``: a ``KeyframeTables`` (packed and uploaded here) or an already uploaded ``SamplerTables``."""
+        dev = self.device
+        assert store.device == dev
+        if isinstance(tables, KeyframeTables):
+            kt = tables
+            tables = SamplerTables(dev, kt.kf_slot.shape[0], kf_stride=kt.kf_slot.shape[1])
+            tables.fill_store(kt)
+            tables.upload()
+        B = tables.n_obj
+        N, S = n_frames * n_pix, self.n1 + self.n2
+        out = out if out is not None else self._outputs(B, N, S, want_u8)
+        a = _lib.SampleArgs()
+        a.store_rgbx, a.store_depth, a.store_inst, a.store_t_wc = _p(store.rgbx), _p(store.depth), _p(store.inst), _p(store.t_wc)
+        tables.bind(a)
+        return self._launch(a, out, B, n_frames, n_pix, store.W, store.H, rays_dir, seed, offset, inject, tables, offset_dev)
+
+
+class SamplerTables:
+    """The per-object tables of one sampler launch in ONE pinned host buffer with a device twin, so a frame needs a
+    single small host->device copy -- and, being persistent, that copy and the launch can sit inside a captured
+    CUDA graph (fill on the host, then ``upload``).
+
+    per-object mode (int64 words): [4][B] pointers rgbs|depths|t_wc|bbox, then int32 pairs n_kf[B] | latest[B][2]
+    store mode      (int32 words): kf_slot[B][KF] | bbox[B][KF][4] (f32 bits) | obj_id[B] | n_kf[B] | latest[B][2]"""
+
+    def __init__(self, device, n_obj: int, kf_stride: int = 0):
+        self.device, self.n_obj, self.kf_stride = torch.device(device), n_obj, kf_stride
+        B, KF = n_obj, kf_stride
+        words64 = 4 * B + (3 * B + 1) // 2 if KF == 0 else (B * KF * 5 + 4 * B + 1) // 2
+        self.host = torch.zeros(words64, dtype=torch.int64)
+        if torch.cuda.is_available():
+            self.host = self.host.pin_memory()
+        self.dev = torch.zeros(words64, dtype=torch.int64, device=self.device)
+
+    def fill_objects(self, sets: Sequence[KeyframeSet]) -> None:
+        B = self.n_obj
+        assert self.kf_stride == 0 and len(sets) == B
+        for o in sets:
             assert o.rgbs_batch.is_contiguous() and o.depth_batch.is_contiguous()
             assert o.t_wc_batch.is_contiguous() and o.bbox.is_contiguous()
             assert o.rgbs_batch.dtype == torch.uint8 and o.depth_batch.dtype == torch.float32
-            assert o.rgbs_batch.device == dev
-        # one pinned staging buffer -> ONE small host->device copy: [4][B] pointers | [B] n_kf + [B][2] latest (int32 pairs)
-        i32 = [o.n_keyframes for o in objects] + [v for o in objects for v in _latest2(o.latest_kf)]
+            assert o.rgbs_batch.device == self.device
+        i32 = [o.n_keyframes for o in sets] + [v for o in sets for v in _latest2(o.latest_kf)]
         if len(i32) & 1:
             i32.append(0)
-        cols = ([o.rgbs_batch.data_ptr() for o in objects] + [o.depth_batch.data_ptr() for o in objects] +
-                [o.t_wc_batch.data_ptr() for o in objects] + [o.bbox.data_ptr() for o in objects])
-        host = torch.tensor(cols + [(i32[k] & 0xffffffff) | (i32[k + 1] << 32) for k in range(0, len(i32), 2)],
-                            dtype=torch.int64)
-        host = host.pin_memory()
-        devbuf = host.to(dev, non_blocking=True)
-        ptrs = devbuf[:4 * B].view(4, B)
-        tail_d = devbuf[4 * B:].view(torch.int32)
-        nkf, latest = tail_d[:B], tail_d[B:3 * B]
-        out = self._outputs(B, N, S, want_u8)
-        a = _lib.SampleArgs()
-        a.rgbs, a.depths, a.t_wc, a.bbox = _p(ptrs[0]), _p(ptrs[1]), _p(ptrs[2]), _p(ptrs[3])
-        a.n_keyframes, a.latest_kf = _p(nkf), _p(latest)
-        return self._launch(a, out, B, n_frames, n_pix, W, H, rays_dir, seed, offset, inject, (host, devbuf))
+        cols = ([o.rgbs_batch.data_ptr() for o in sets] + [o.depth_batch.data_ptr() for o in sets] +
+                [o.t_wc_batch.data_ptr() for o in sets] + [o.bbox.data_ptr() for o in sets])
+        self.host.copy_(torch.tensor(cols + [(i32[k] & 0xffffffff) | (i32[k + 1] << 32) for k in range(0, len(i32), 2)],
+                                     dtype=torch.int64))
 
-    def sample_store(self, store, tables: "KeyframeTables", n_frames: int, n_pix: int, rays_dir: torch.Tensor,
-                     seed: int = 0, offset: int = 0, inject: Optional[Dict[str, torch.Tensor]] = None,
-                     want_u8: bool = False) -> Dict[str, torch.Tensor]:
-        """Shared keyframe store (keyframes.FrameStore): frames stored once, per-object (slot, bbox) tables,
-        pixel state derived from the instance image.  Same draws / outputs as ``sample`` on per-object copies."""
-        dev = self.device
-        assert store.device == dev
-        B, KF = tables.kf_slot.shape
-        N, S = n_frames * n_pix, self.n1 + self.n2
-        t = tables.to_device(dev)
-        out = self._outputs(B, N, S, want_u8)
-        a = _lib.SampleArgs()
-        a.store_rgbx, a.store_depth, a.store_inst, a.store_t_wc = _p(store.rgbx), _p(store.depth), _p(store.inst), _p(store.t_wc)
-        a.kf_slot, a.kf_bbox, a.obj_id, a.kf_stride = _p(t["kf_slot"]), _p(t["kf_bbox"]), _p(t["obj_id"]), KF
-        a.n_keyframes, a.latest_kf = _p(t["n_kf"]), _p(t["latest"])
-        return self._launch(a, out, B, n_frames, n_pix, store.W, store.H, rays_dir, seed, offset, inject, t)
+    def fill_store(self, kt: "KeyframeTables") -> None:
+        B, KF = self.n_obj, self.kf_stride
+        assert kt.kf_slot.shape == (B, KF)
+        h = self.host.view(torch.int32)
+        o = 0
+        for t in (kt.kf_slot, kt.kf_bbox.view(torch.int32), kt.obj_id, kt.n_kf, kt.latest):
+            h[o:o + t.numel()] = t.reshape(-1)
+            o += t.numel()
+
+    def upload(self) -> None:
+        self.dev.copy_(self.host, non_blocking=True)
+
+    def bind(self, a) -> None:
+        B, KF = self.n_obj, self.kf_stride
+        if KF == 0:
+            ptrs = self.dev[:4 * B].view(4, B)
+            tail = self.dev[4 * B:].view(torch.int32)
+            a.rgbs, a.depths, a.t_wc, a.bbox = _p(ptrs[0]), _p(ptrs[1]), _p(ptrs[2]), _p(ptrs[3])
+            a.n_keyframes, a.latest_kf = _p(tail[:B]), _p(tail[B:3 * B])
+        else:
+            d = self.dev.view(torch.int32)
+            o1 = B * KF
+            o2 = o1 + B * KF * 4
+            a.kf_slot, a.kf_bbox, a.obj_id, a.kf_stride = _p(d[:o1]), _p(d[o1:o2]), _p(d[o2:o2 + B]), KF
+            a.n_keyframes, a.latest_kf = _p(d[o2 + B:o2 + 2 * B]), _p(d[o2 + 2 * B:o2 + 4 * B])
 
 
 def _latest2(q):
@@ -159,17 +213,3 @@ class KeyframeTables:
         self.latest = torch.as_tensor(latest, dtype=torch.int32).contiguous()            # [B,2]
         B, KF = self.kf_slot.shape
         assert self.kf_bbox.shape == (B, KF, 4) and self.obj_id.shape == (B,) and self.latest.shape == (B, 2)
-
-    def to_device(self, dev):
-        parts = [("kf_slot", self.kf_slot), ("kf_bbox", self.kf_bbox.view(torch.int32)), ("obj_id", self.obj_id),
-                 ("n_kf", self.n_kf), ("latest", self.latest)]
-        flat = torch.cat([t.reshape(-1) for _, t in parts])
-        if torch.cuda.is_available():
-            flat = flat.pin_memory()
-        d = flat.to(dev, non_blocking=True)
-        out, o = {"_flat": d, "_host": flat}, 0
-        for name, t in parts:
-            v = d[o:o + t.numel()]
-            out[name] = v.view(torch.float32) if name == "kf_bbox" else v
-            o += t.numel()
-        return out
