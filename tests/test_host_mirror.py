@@ -61,3 +61,39 @@ def test_no_cpu_fallback():
         from vmap_b200.ensemble import VmapEnsemble
         with pytest.raises(Exception):
             VmapEnsemble(2, device="cpu")
+
+
+def test_sampler_tables_packing_round_trip():
+    """SamplerTables packs the per-object tables of a sampler launch into one (pinned) buffer; the views handed to
+    the C ABI must read back exactly what was filled in, in both keyframe layouts (host logic, no GPU)."""
+    import ctypes as C
+    import numpy as np
+    from vmap_b200 import _lib
+    from vmap_b200.sampler import KeyframeSet, KeyframeTables, SamplerTables
+    B, KF = 3, 5
+    # store mode
+    rng = np.random.default_rng(0)
+    kt = KeyframeTables(rng.integers(0, 9, (B, KF)).astype(np.int32), rng.random((B, KF, 4)).astype(np.float32),
+                        [4, 7, 9], [5, 3, 2], [[3, 4], [1, 2], [0, 1]])
+    t = SamplerTables("cpu", B, kf_stride=KF)
+    t.fill_store(kt)
+    t.upload()
+    a = _lib.SampleArgs()
+    t.bind(a)
+    rd = lambda ptr, n, ct: np.ctypeslib.as_array(C.cast(ptr, C.POINTER(ct)), shape=(n,)).copy()
+    assert rd(a.kf_slot, B * KF, C.c_int).tolist() == kt.kf_slot.reshape(-1).tolist()
+    assert np.array_equal(rd(a.kf_bbox, B * KF * 4, C.c_float), kt.kf_bbox.reshape(-1).numpy())
+    assert rd(a.obj_id, B, C.c_int).tolist() == [4, 7, 9] and rd(a.n_keyframes, B, C.c_int).tolist() == [5, 3, 2]
+    assert rd(a.latest_kf, 2 * B, C.c_int).tolist() == [3, 4, 1, 2, 0, 1] and a.kf_stride == KF
+    # per-object mode
+    sets = [KeyframeSet(torch.zeros(KF, 4, 3, 4, dtype=torch.uint8), torch.zeros(KF, 4, 3), torch.zeros(KF, 4, 4),
+                        torch.zeros(KF, 4), n, [n - 2, n - 1]) for n in (5, 4, 3)]
+    t2 = SamplerTables("cpu", B)
+    t2.fill_objects(sets)
+    t2.upload()
+    a2 = _lib.SampleArgs()
+    t2.bind(a2)
+    assert rd(a2.rgbs, B, C.c_longlong).tolist() == [s.rgbs_batch.data_ptr() for s in sets]
+    assert rd(a2.bbox, B, C.c_longlong).tolist() == [s.bbox.data_ptr() for s in sets]
+    assert rd(a2.n_keyframes, B, C.c_int).tolist() == [5, 4, 3]
+    assert rd(a2.latest_kf, 2 * B, C.c_int).tolist() == [3, 4, 2, 3, 1, 2]
