@@ -67,6 +67,12 @@ def test_frame_graph_matches_eager_loop(use_store):
         assert int(fl.counter) == 7 + 3 and ens.step_count == 3 * n_iter and int(ens.step_counter) == 3 * n_iter
         results.append((torch.stack(losses).cpu(), draws, ens.params.clone()))
     (l_e, d_e, p_e), (l_g, d_g, p_g) = results
+    # the frame loop's first draw == a plain sampler call with the same seed / offset, for EVERY object
+    smp = BatchedSampler(DEV, 1, 9)
+    ref = (smp.sample_store(store, kt, n_frames, n_pix, rays, seed=5, offset=7) if use_store
+           else smp.sample(sets, n_frames, n_pix, rays, seed=5, offset=7))
+    assert torch.equal(ref["pcs"], d_e[0]) and torch.equal(ref["pcs"], d_g[0])
+    assert float(ref["z"].min()) >= 0.0 and float(ref["gt_depth"].max()) <= 3.5 + 1e-6
     for a, b in zip(d_e, d_g):
         assert torch.equal(a, b)                       # same draws frame by frame (device draw counter)
     assert not torch.equal(d_g[0], d_g[1])             # and fresh ones every frame

@@ -102,7 +102,7 @@ class BatchedSampler:
         CUDA-graph capture of a whole frame (frame.FrameLoop); with ``tables`` the caller has already filled and
         uploaded them and ``objects`` only provides the image size."""
         dev = self.device
-        B = len(objects)
+        B = tables.n_obj if tables is not None else len(objects)
         N, S = n_frames * n_pix, self.n1 + self.n2
         W, H = objects[0].rgbs_batch.shape[1], objects[0].rgbs_batch.shape[2]
         if tables is None:
