@@ -37,12 +37,10 @@ class FrameLoop:
         self.counter = torch.full((1,), first_offset, dtype=torch.int64, device=dev)     # sampler draw counter
         self.losses = torch.zeros(n_iter, dtype=torch.float32, device=dev)
         self.graph: Optional[torch.cuda.CUDAGraph] = None
-        self._size_from: Optional[List[KeyframeSet]] = None
 
     # ---- per-frame host work: only the small tables ------------------------------------------------------
     def set_objects(self, sets: Sequence[KeyframeSet]) -> None:
         self.tables.fill_objects(sets)
-        self._size_from = list(sets)[:1]
 
     def set_store_tables(self, kt: KeyframeTables) -> None:
         self.tables.fill_store(kt)
@@ -55,7 +53,7 @@ class FrameLoop:
             s.sample_store(self.store, self.tables, self.n_frames, self.n_pix, self.rays_dir, seed=self.seed,
                            out=self.out, offset_dev=self.counter)
         else:
-            s.sample(self._size_from, self.n_frames, self.n_pix, self.rays_dir, seed=self.seed,
+            s.sample(None, self.n_frames, self.n_pix, self.rays_dir, seed=self.seed,
                      tables=self.tables, out=self.out, offset_dev=self.counter)
         self.counter += 1
         for it in range(self.n_iter):

@@ -100,16 +100,16 @@ class BatchedSampler:
         """Per-object keyframe buffers (the reference's layout, vmap.py:137-176).
         ``tables`` / ``out`` / ``offset_dev``: persistent table + output buffers and a device draw counter, for
         CUDA-graph capture of a whole frame (frame.FrameLoop); with ``tables`` the caller has already filled and
-        uploaded them and ``objects`` only provides the image size."""
+        uploaded them and ``objects`` is ignored."""
         dev = self.device
-        B = tables.n_obj if tables is not None else len(objects)
         N, S = n_frames * n_pix, self.n1 + self.n2
-        W, H = objects[0].rgbs_batch.shape[1], objects[0].rgbs_batch.shape[2]
         if tables is None:
-            tables = SamplerTables(dev, B)
+            tables = SamplerTables(dev, len(objects))
             tables.fill_objects(objects)
             tables.upload()
+        B, (W, H) = tables.n_obj, tables.image_wh           # the tables, not ``objects``, define the launch
         out = out if out is not None else self._outputs(B, N, S, want_u8)
+        assert out["pcs"].shape == (B, N, S, 3) and out["sem"].shape == (B, N)
         a = _lib.SampleArgs()
         tables.bind(a)
         return self._launch(a, out, B, n_frames, n_pix, W, H, rays_dir, seed, offset, inject, tables, offset_dev)
@@ -130,6 +130,7 @@ class BatchedSampler:
         B = tables.n_obj
         N, S = n_frames * n_pix, self.n1 + self.n2
         out = out if out is not None else self._outputs(B, N, S, want_u8)
+        assert out["pcs"].shape == (B, N, S, 3) and out["sem"].shape == (B, N)
         a = _lib.SampleArgs()
         a.store_rgbx, a.store_depth, a.store_inst, a.store_t_wc = _p(store.rgbx), _p(store.depth), _p(store.inst), _p(store.t_wc)
         tables.bind(a)
@@ -152,6 +153,7 @@ class SamplerTables:
         if torch.cuda.is_available():
             self.host = self.host.pin_memory()
         self.dev = torch.zeros(words64, dtype=torch.int64, device=self.device)
+        self.image_wh = None            # (W, H) of the per-object keyframe images (per-object mode)
 
     def fill_objects(self, sets: Sequence[KeyframeSet]) -> None:
         B = self.n_obj
@@ -161,6 +163,7 @@ class SamplerTables:
             assert o.t_wc_batch.is_contiguous() and o.bbox.is_contiguous()
             assert o.rgbs_batch.dtype == torch.uint8 and o.depth_batch.dtype == torch.float32
             assert o.rgbs_batch.device == self.device
+        self.image_wh = (int(sets[0].rgbs_batch.shape[1]), int(sets[0].rgbs_batch.shape[2]))
         i32 = [o.n_keyframes for o in sets] + [v for o in sets for v in _latest2(o.latest_kf)]
         if len(i32) & 1:
             i32.append(0)
