@@ -4,9 +4,13 @@
 //
 //   D[M][N] (+)= A[M][K] * B[N][K]^T        fp16 operands, fp32 accumulate in TMEM
 //
-// * 128 x 128 output tile per CTA, K in chunks of 64, 3-stage TMA -> mbarrier -> tcgen05.mma pipeline:
-//   warp 4 = TMA producer (one elected lane), warp 5 = MMA issuer, warps 0..3 = epilogue
-//   (TMEM -> registers -> global).  96 KB of shared memory and 128 TMEM columns: two CTAs per SM.
+// Two kernels share the operand conventions below:
+//   k_gemm_umma  generic persistent kernel: 128 x 128 output tiles, K in chunks of 64, 3-stage TMA -> mbarrier ->
+//                tcgen05.mma pipeline, warp 4 = TMA producer (one elected lane), warp 5 = MMA issuer, warps 0..3 =
+//                epilogue; two TMEM accumulators (2 x 128 columns) so tile i+1's MMAs overlap tile i's epilogue;
+//                107 KB of shared memory: two CTAs per SM.  Used for wgrad (split-K over points, atomics) and for the
+//                forward layers whose weights exceed the weight-stationary budget.
+//   k_gemm_ws    weight-stationary kernel for the skinny forward / dgrad GEMMs (see its header further down).
 // * Operand stages use the 128-byte-swizzle canonical layouts, written by TMA (CU_TENSOR_MAP_SWIZZLE_128B,
 //   128-byte inner box so the TMA engine moves full lines; a first version with 16-byte inner boxes into the
 //   SWIZZLE_NONE layout was TMA-bound at ~150 TFLOP/s):
