@@ -66,3 +66,44 @@ def test_oracle_matches_live_reference_step(n_obj, hidden, n_rays, n_samples, sc
         assert abs(a - b) <= 5e-6 * abs(b) + 1e-7
     for k in vo.ALL_KEYS:
         assert rel_l2(orc.params[k], p_ref[k]) < 2e-6, k
+
+
+@pytest.mark.parametrize("seed,n_kf,n_frames,n_samples,n1", [(31, 7, 9, 11, 1), (32, 3, 6, 5, 5), (33, 1, 4, 7, 1),
+                                                             (34, 8, 20, 3, 1), (35, 4, 5, 16, 5)])
+def test_sampler_oracle_matches_live_reference(seed, n_kf, n_frames, n_samples, n1):
+    """sceneObject.get_training_samples (vmap.py:319-459) run live vs oracle/sampler_oracle.py with the reference's RNG
+    call order reproduced: integer outputs and z bit-exact."""
+    import numpy as np
+    from oracle import sampler_oracle as so
+    vmap_mod = _refload.load("vmap")
+    W, H, KF = 56, 40, 8
+    g = torch.Generator().manual_seed(seed)
+    rgbs = torch.randint(0, 256, (KF, W, H, 4), generator=g).to(torch.uint8)
+    rgbs[..., 3] = (torch.rand(KF, W, H, generator=g) * 3).long().clamp(0, 2).to(torch.uint8)
+    depth = torch.rand(KF, W, H, generator=g) * 4 + 0.5
+    depth[torch.rand(KF, W, H, generator=g) < 0.15] = 0.0
+    twc = torch.eye(4).repeat(KF, 1, 1)
+    twc[:, :3, 3] = torch.rand(KF, 3, generator=g) - 0.5
+    bbox = torch.empty(KF, 4)
+    bbox[:, 0] = torch.randint(0, W // 2, (KF,), generator=g).float()
+    bbox[:, 1] = bbox[:, 0] + torch.randint(4, W // 2, (KF,), generator=g).float()
+    bbox[:, 2] = torch.randint(0, H // 2, (KF,), generator=g).float()
+    bbox[:, 3] = bbox[:, 2] + torch.randint(4, H // 2, (KF,), generator=g).float()
+    rays = so.camera_ray_dirs(W, H, 60.0, 60.0, W / 2 - 0.5, H / 2 - 0.5)
+    latest = [n_kf - 2, n_kf - 1] if n_kf >= 2 else [0]
+    obj = object.__new__(vmap_mod.sceneObject)          # skip __init__ (builds a Trainer / open3d)
+    obj.n_keyframes, obj.data_device, obj.lastest_kf_queue = n_kf, "cpu", list(latest)
+    obj.bbox, obj.rgbs_batch, obj.depth_batch, obj.t_wc_batch = bbox, rgbs, depth, twc
+    obj.n_bins_cam2surface, obj.n_bins, obj.surface_eps, obj.stop_eps = n1, 9, 0.1, 0.05
+    obj.min_bound, obj.max_bound = 0.0, 8.0
+    obj.this_obj, obj.other_obj, obj.unknown_obj = 1, 0, 2
+    obj.obj_center = torch.tensor(0.0)
+    torch.manual_seed(seed + 1)
+    r_rgb, r_depth, r_valid, r_lab, r_pcs, r_z = obj.get_training_samples(n_frames, n_samples, rays)
+    cfg = so.SamplerCfg(n_bins_cam2surface=n1)
+    torch.manual_seed(seed + 1)
+    rnd = so.draw_randoms_reference_order(None, n_kf, latest, n_frames, n_samples, bbox, rgbs, depth, cfg)
+    rgb, dep, valid, lab, pcs, z = so.sample_from_randoms(rnd, rgbs, depth, twc, bbox, rays, cfg)
+    assert torch.equal(rgb, r_rgb) and torch.equal(dep, r_depth) and torch.equal(valid, r_valid) and torch.equal(lab, r_lab)
+    assert torch.equal(z, r_z)
+    np.testing.assert_allclose(pcs.numpy(), r_pcs.numpy(), rtol=0, atol=1e-6)
