@@ -107,3 +107,48 @@ def test_sampler_oracle_matches_live_reference(seed, n_kf, n_frames, n_samples, 
     assert torch.equal(rgb, r_rgb) and torch.equal(dep, r_depth) and torch.equal(valid, r_valid) and torch.equal(lab, r_lab)
     assert torch.equal(z, r_z)
     np.testing.assert_allclose(pcs.numpy(), r_pcs.numpy(), rtol=0, atol=1e-6)
+
+
+@pytest.mark.parametrize("kf_step,buf,n_frames_seen,seed", [(3, 6, 40, 1), (1, 4, 25, 2), (5, 8, 60, 3)])
+def test_keyframe_policy_matches_live_reference(kf_step, buf, n_frames_seen, seed, monkeypatch):
+    """vmap_b200.vmap.sceneObject.append_keyframe / prune_keyframe vs the reference's (vmap.py:208-268), fed the same
+    frames and the same ``random`` stream: slot choice, keyframe count, latest queue, id map and buffer contents."""
+    import random
+    import types
+    from oracle._refload import _Bidict
+    from vmap_b200 import vmap as vm
+    ref_mod = _refload.load("vmap")
+    monkeypatch.setattr(vm.trainer_mod, "Trainer", lambda cfg: types.SimpleNamespace())
+    W, H = 6, 5
+    cfg = types.SimpleNamespace(do_bg=False, data_device="cpu", training_device="cpu", obj_scale=2.0, bg_scale=5.0,
+                                hidden_feature_size=32, hidden_feature_size_bg=128, n_bins_cam2surface=1,
+                                n_bins_cam2surface_bg=5, keyframe_step=kf_step, keyframe_step_bg=kf_step, min_depth=0.0,
+                                max_depth=8.0, n_bins=9, n_unidir_funcs=5, surface_eps=0.1, stop_eps=0.05,
+                                keyframe_buffer_size=buf)
+
+    def frame(fid):
+        g = torch.Generator().manual_seed(1000 * seed + fid)
+        return (torch.randint(0, 255, (W, H, 3), dtype=torch.uint8, generator=g), torch.rand(W, H, generator=g),
+                torch.randint(0, 3, (W, H), dtype=torch.uint8, generator=g), torch.tensor([0., float(fid % W), 0., float(fid % H)]),
+                torch.eye(4) * (fid + 1))
+
+    rgb, depth, mask, bbox, T = frame(0)
+    mine = vm.sceneObject(cfg, 7, rgb, depth, mask, bbox, T, 0)
+    ref = object.__new__(ref_mod.sceneObject)               # the reference __init__ builds a Trainer / needs open3d
+    ref.n_keyframes, ref.kf_pointer, ref.keyframe_buffer_size = 1, None, buf
+    ref.kf_id_dict, ref.kf_buffer_full, ref.frame_cnt, ref.lastest_kf_queue = _Bidict({0: 0}), False, 0, []
+    ref.keyframe_step, ref.rgb_idx, ref.state_idx = kf_step, slice(0, 3), slice(3, 4)
+    ref.bbox = torch.empty(buf, 4); ref.rgbs_batch = torch.empty(buf, W, H, 4, dtype=torch.uint8)
+    ref.depth_batch = torch.empty(buf, W, H); ref.t_wc_batch = torch.empty(buf, 4, 4)
+    ref.bbox[0] = bbox; ref.rgbs_batch[0, :, :, :3] = rgb; ref.rgbs_batch[0, :, :, 3:4] = mask[..., None]
+    ref.depth_batch[0] = depth; ref.t_wc_batch[0] = T
+    for fid in range(1, n_frames_seen):
+        rgb, depth, mask, bbox, T = frame(fid)
+        random.seed(fid); mine.append_keyframe(rgb, depth, mask, bbox, T, fid)
+        random.seed(fid); ref.append_keyframe(rgb, depth, mask, bbox, T, fid)
+        assert mine.n_keyframes == ref.n_keyframes and mine.kf_pointer == ref.kf_pointer, fid
+        assert mine.lastest_kf_queue == ref.lastest_kf_queue and mine.frame_cnt == ref.frame_cnt
+        assert dict(mine.kf_id_dict) == dict(ref.kf_id_dict) and mine.kf_buffer_full == ref.kf_buffer_full
+        n = max(mine.n_keyframes, (mine.kf_pointer or 0) + 1)
+        assert torch.equal(mine.rgbs_batch[:n], ref.rgbs_batch[:n]) and torch.equal(mine.depth_batch[:n], ref.depth_batch[:n])
+        assert torch.equal(mine.t_wc_batch[:n], ref.t_wc_batch[:n]) and torch.equal(mine.bbox[:n], ref.bbox[:n])
