@@ -152,3 +152,20 @@ def test_keyframe_policy_matches_live_reference(kf_step, buf, n_frames_seen, see
         n = max(mine.n_keyframes, (mine.kf_pointer or 0) + 1)
         assert torch.equal(mine.rgbs_batch[:n], ref.rgbs_batch[:n]) and torch.equal(mine.depth_batch[:n], ref.depth_batch[:n])
         assert torch.equal(mine.t_wc_batch[:n], ref.t_wc_batch[:n]) and torch.equal(mine.bbox[:n], ref.bbox[:n])
+
+
+def test_module_surface_matches_live_reference():
+    """state_dict keys / shapes of OccupancyMap and UniDirsEmbed, the icosahedron directions, and cameraInfo's ray cache
+    against the live reference classes (model.py:17-52, embedding.py:44-80, vmap.py:494-524)."""
+    import types
+    from vmap_b200 import embedding as my_emb, model as my_model, vmap as my_vmap
+    ref_model, ref_emb, ref_vmap = _refload.load("model", "embedding", "vmap")
+    for hidden in (32, 128, 256):
+        a = my_model.OccupancyMap(87, 42, hidden_size=hidden).state_dict()
+        b = ref_model.OccupancyMap(87, 42, hidden_size=hidden).state_dict()
+        assert list(a) == list(b) and all(a[k].shape == b[k].shape for k in a)
+    pa, pb = my_emb.UniDirsEmbed(max_deg=5, scale=2.0), ref_emb.UniDirsEmbed(max_deg=5, scale=2.0)
+    assert list(pa.state_dict()) == list(pb.state_dict())
+    assert torch.equal(pa.B_layer.weight.detach(), pb.B_layer.weight.detach()) and float(pa.scale) == float(pb.scale)
+    cfg = types.SimpleNamespace(data_device="cpu", W=37, H=23, fx=31.5, fy=29.25, cx=18.0, cy=11.5)
+    assert torch.equal(my_vmap.cameraInfo(cfg).rays_dir_cache, ref_vmap.cameraInfo(cfg).rays_dir_cache)
