@@ -169,3 +169,36 @@ def test_module_surface_matches_live_reference():
     assert torch.equal(pa.B_layer.weight.detach(), pb.B_layer.weight.detach()) and float(pa.scale) == float(pb.scale)
     cfg = types.SimpleNamespace(data_device="cpu", W=37, H=23, fx=31.5, fy=29.25, cx=18.0, cy=11.5)
     assert torch.equal(my_vmap.cameraInfo(cfg).rays_dir_cache, ref_vmap.cameraInfo(cfg).rays_dir_cache)
+
+
+@pytest.mark.parametrize("W,H,n_inst,seed", [(96, 64, 9, 41), (200, 150, 25, 42), (64, 96, 5, 43)])
+def test_ingest_oracle_matches_live_reference_loader(W, H, n_inst, seed):
+    """oracle/ingest_oracle.replica_frame vs dataset.Replica.__getitem__ (dataset.py:80-141) run live on a synthetic
+    Replica-format directory (written under the repo's scratch area and removed afterwards)."""
+    import os
+    import shutil
+    import tempfile
+    import types
+    import numpy as np
+    cv2 = pytest.importorskip("cv2")
+    from oracle import ingest_oracle as io
+    dataset = _refload.load("dataset")
+    inst, cls = io.synthetic_instance_frame(W, H, n_inst, seed)
+    root = tempfile.mkdtemp(prefix="_ds_", dir=os.path.dirname(os.path.abspath(io.__file__)))
+    try:
+        for d in ("rgb", "depth", "semantic_instance", "semantic_class"):
+            os.makedirs(os.path.join(root, d))
+        rng = np.random.default_rng(seed)
+        cv2.imwrite(os.path.join(root, "rgb", "rgb_0.png"), rng.integers(0, 255, (H, W, 3), dtype=np.uint8))
+        cv2.imwrite(os.path.join(root, "depth", "depth_0.png"), rng.integers(500, 4000, (H, W)).astype(np.uint16))
+        cv2.imwrite(os.path.join(root, "semantic_instance", "semantic_instance_0.png"), inst.T.astype(np.uint16))
+        cv2.imwrite(os.path.join(root, "semantic_class", "semantic_class_0.png"), cls.T.astype(np.uint16))
+        np.savetxt(os.path.join(root, "traj_w_c.txt"), np.eye(4).reshape(1, 16), delimiter=" ")
+        ds = dataset.Replica(types.SimpleNamespace(imap_mode=False, dataset_dir=root, depth_scale=1000.0, max_depth=8.0))
+        sample = ds[0]
+    finally:
+        shutil.rmtree(root, ignore_errors=True)
+    ref_bbox = {int(k): [int(x) for x in np.asarray(v).reshape(-1)] for k, v in sample["bbox_dict"].items()}
+    bbox_dict, obj = io.replica_frame(inst, cls, set(ds.background_cls_list), ds.bbox_scale)
+    assert {k: v.tolist() for k, v in bbox_dict.items()} == ref_bbox
+    assert np.array_equal(obj, np.asarray(sample["obj"]).astype(np.int32))
