@@ -152,10 +152,15 @@ __global__ void __launch_bounds__(256) k_sample_gather(SampleParams a, unsigned 
 }
 
 // Pass 2 (grid = ray chunks x objects): per-ray sample depths and 3-D points (vmap.py:366-459)
+// N1 / N2 > 0: compile-time bin counts (the shipped object (1, 9) and background (5, 9) configurations): every loop
+// unrolls and the per-ray random / normal arrays live in registers; 0 = run-time counts (arrays in local memory).
+template <int N1, int N2>
 __global__ void __launch_bounds__(256) k_sample_points(SampleParams a, const unsigned int* __restrict__ smax) {
   const int b = blockIdx.y;
   const int N = a.n_frames * a.n_pix;
-  const int S = a.n1 + a.n2;
+  const int n1 = N1 ? N1 : a.n1, n2 = N2 ? N2 : a.n2;
+  const int S = n1 + n2;
+  constexpr int SMAX = (N1 && N2) ? N1 + N2 : 32, N2MAX = N2 ? N2 : 32;
   const float max_bound = fkey_inv(smax[b]);
   // a thread owns a ray (S x 16 B of output), so direct stores would touch 32 lines per instruction: the block's
   // rays are consecutive in memory, results are staged in shared memory and written out as one coalesced span
@@ -175,22 +180,27 @@ __global__ void __launch_bounds__(256) k_sample_points(SampleParams a, const uns
     const bool invalid = d <= a.min_bound;
     const bool this_obj = (state == 1) && !invalid;
 
-    float uz[32], nz[32];
+    float uz[SMAX], nz[N2MAX];
     if (a.inj_u_z) {
+#pragma unroll
       for (int s = 0; s < S; ++s) uz[s] = a.inj_u_z[o * S + s];
     } else {
+#pragma unroll
       for (int c = 0; c * 4 < S; ++c) {
         uint32_t q[4];
         philox4x32_10((uint32_t)i * 8u + c, 2u, (uint32_t)b, sample_offset(a), k0, k1, q);
-        for (int j = 0; j < 4 && c * 4 + j < S; ++j) uz[c * 4 + j] = u01(q[j]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) if (c * 4 + j < S) uz[c * 4 + j] = u01(q[j]);
       }
     }
     if (this_obj) {
       if (a.inj_nrm) {
-        for (int s = 0; s < a.n2; ++s) nz[s] = a.inj_nrm[o * a.n2 + s];
+#pragma unroll
+        for (int s = 0; s < n2; ++s) nz[s] = a.inj_nrm[o * n2 + s];
       } else {
         const float sd = a.eps / 3.0f;                            // vmap.py:432 delta/3
-        for (int c = 0; c * 4 < a.n2; ++c) {
+#pragma unroll
+        for (int c = 0; c * 4 < n2; ++c) {
           uint32_t q[4];
           philox4x32_10((uint32_t)i * 8u + c, 3u, (uint32_t)b, sample_offset(a), k0, k1, q);
           const float r0 = sqrtf(-2.f * logf(1.f - u01(q[0]))), r1 = sqrtf(-2.f * logf(1.f - u01(q[2])));
@@ -198,14 +208,26 @@ __global__ void __launch_bounds__(256) k_sample_points(SampleParams a, const uns
           sincospif(2.f * u01(q[1]), &s0, &c0);
           sincospif(2.f * u01(q[3]), &s1, &c1);
           const float g[4] = {r0 * c0, r0 * s0, r1 * c1, r1 * s1};
-          for (int j = 0; j < 4 && c * 4 + j < a.n2; ++j) nz[c * 4 + j] = g[j] * sd;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) if (c * 4 + j < n2) nz[c * 4 + j] = g[j] * sd;
         }
       }
-      for (int x = 1; x < a.n2; ++x) {                            // .sort() (vmap.py:81)
-        const float v = nz[x];
-        int y = x - 1;
-        while (y >= 0 && nz[y] > v) { nz[y + 1] = nz[y]; --y; }
-        nz[y + 1] = v;
+      if (N2) {                                                   // .sort() (vmap.py:81): odd-even transposition network,
+#pragma unroll                                                    // static indices only (registers)
+        for (int round = 0; round < N2MAX; ++round) {
+#pragma unroll
+          for (int x = round & 1; x + 1 < N2MAX; x += 2) {
+            const float lo = fminf(nz[x], nz[x + 1]), hi = fmaxf(nz[x], nz[x + 1]);
+            nz[x] = lo; nz[x + 1] = hi;
+          }
+        }
+      } else {
+        for (int x = 1; x < n2; ++x) {                            // insertion sort
+          const float v = nz[x];
+          int y = x - 1;
+          while (y >= 0 && nz[y] > v) { nz[y + 1] = nz[y]; --y; }
+          nz[y + 1] = v;
+        }
       }
     }
 
@@ -217,17 +239,18 @@ __global__ void __launch_bounds__(256) k_sample_points(SampleParams a, const uns
     const float dw2 = fmaf(T[10], dc[2], fmaf(T[9], dc[1], T[8] * dc[0]));
     const float o0 = T[3], o1 = T[7], o2 = T[11];                              // vmap.py:39
 
+#pragma unroll
     for (int s = 0; s < S; ++s) {
       float zz;
       if (invalid) {
         zz = strat(a.min_bound, max_bound, limS, S, s, uz[s]);                 // vmap.py:400-404
-      } else if (s < a.n1) {
-        zz = strat(a.min_bound, __fsub_rn(d, a.eps), lim1, a.n1, s, uz[s]);    // vmap.py:413-415
+      } else if (s < n1) {
+        zz = strat(a.min_bound, __fsub_rn(d, a.eps), lim1, n1, s, uz[s]);    // vmap.py:413-415
       } else if (this_obj) {
-        const float bn = fminf(fmaxf(nz[s - a.n1], -a.eps), a.eps);            // vmap.py:82
+        const float bn = fminf(fmaxf(nz[s < n1 ? 0 : s - n1], -a.eps), a.eps);            // vmap.py:82
         zz = __fadd_rn(d, bn);                                                 // vmap.py:83
       } else {
-        zz = strat(__fsub_rn(d, a.eps), __fadd_rn(d, a.oeps), lim2, a.n2, s - a.n1, uz[s]);   // vmap.py:447-450
+        zz = strat(__fsub_rn(d, a.eps), __fadd_rn(d, a.oeps), lim2, n2, s - n1, uz[s]);   // vmap.py:447-450
       }
       s_z[threadIdx.x * S + s] = zz;
       float* pc = s_p + (threadIdx.x * S + s) * 3;                             // vmap.py:455

@@ -331,10 +331,15 @@ int vmb_sample(vmb_handle* h, const vmb_sample_args* a, void* stream) {
   const int smem_pts = 256 * (a->n_bins_cam2surface + a->n_bins) * 16;      // staged z + points of 256 rays
   static bool attr_set[64] = {};
   if (!attr_set[h->device & 63]) {
-    CUDA_TRY(h, cudaFuncSetAttribute(k_sample_points, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 32 * 16));
+    CUDA_TRY(h, cudaFuncSetAttribute(k_sample_points<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 32 * 16));
+    CUDA_TRY(h, cudaFuncSetAttribute(k_sample_points<1, 9>, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 32 * 16));
+    CUDA_TRY(h, cudaFuncSetAttribute(k_sample_points<5, 9>, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 32 * 16));
     attr_set[h->device & 63] = true;
   }
-  k_sample_points<<<dim3(chunks, a->n_obj), 256, smem_pts, st>>>(p, h->d_smax);
+  const dim3 grid2(chunks, a->n_obj);
+  if (a->n_bins_cam2surface == 1 && a->n_bins == 9)      k_sample_points<1, 9><<<grid2, 256, smem_pts, st>>>(p, h->d_smax);   // objects
+  else if (a->n_bins_cam2surface == 5 && a->n_bins == 9) k_sample_points<5, 9><<<grid2, 256, smem_pts, st>>>(p, h->d_smax);   // background
+  else                                                   k_sample_points<0, 0><<<grid2, 256, smem_pts, st>>>(p, h->d_smax);
   CUDA_TRY(h, cudaGetLastError());
   return VMB_OK;
 }
