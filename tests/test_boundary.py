@@ -63,3 +63,19 @@ def test_structs_match_header_field_order():
     names = re.findall(r"[\s\*]([a-z_0-9]+)\s*[;,]", body)
     names = [n for n in names if n not in ("vmb_step_args",)]
     assert names == [f[0] for f in _lib.StepArgs._fields_]
+
+
+def test_bench_product_arm_fails_loudly_without_gpu():
+    """bench.py's product arm must never fall back to the CPU (the oracle is only the checker / the reference arm)."""
+    import os
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.is_available():
+        import pytest
+        pytest.skip("a GPU is present")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=300, cwd=root)
+    assert r.returncode != 0 and "no CPU fallback" in (r.stdout + r.stderr)
+    assert "{" not in r.stdout          # no JSON line, no number
