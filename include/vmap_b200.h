@@ -40,7 +40,8 @@ enum {
 enum {
   VMB_IMPL_AUTO = 0,
   VMB_IMPL_FP32 = 1,    /* CUDA-core fp32 kernel, any hidden size (parity anchor)            */
-  VMB_IMPL_UMMA = 2,    /* tcgen05/TMEM fp16-operand fused kernel, hidden = 32 (the fast path) */
+  VMB_IMPL_UMMA = 2,    /* tcgen05/TMEM fp16-operand fused kernel, hidden = 32 (the fast path): counts, step,
+                           gradient reduction and (with fuse_adam) AdamW in ONE launch, n_samples <= 32        */
   VMB_IMPL_LAYERWISE = 3 /* tcgen05 GEMM per layer over all points, hidden = 64/128/256 (bg / iMAP) */
 };
 
@@ -91,7 +92,7 @@ typedef struct vmb_step_args {
   const float* params;              /* [B][stride] fp32 master weights                     */
   const void*  image;               /* [B][image_bytes] fp16 weight image (UMMA path) or 0 */
   const float* scale;               /* [B] obj_scale buffer (embedding.py:80)              */
-  float* grads;                     /* [B][stride], ACCUMULATED into (zero on entry; vmb_adam re-zeroes) */
+  float* grads;                     /* [B][stride], ACCUMULATED into (zero on entry; vmb_adam re-zeroes); unused with fuse_adam on hidden 32 */
   float* loss_terms;                /* [B][4] L_depth, L_colour, L_opacity, weighted total (overwritten) */
   float* r_depth;                   /* optional [B][R]      rendered depth                 */
   float* r_var;                     /* optional [B][R]      rendered variance              */
@@ -103,9 +104,22 @@ typedef struct vmb_step_args {
   float colour_scaling;             /* 5.0  (loss.py:6)                                    */
   float opacity_scaling;            /* 10.0 (loss.py:6)                                    */
   int   backward;                   /* 1 = forward+backward, 0 = forward/loss only         */
-  int   reserved;
+  int   fuse_adam;                  /* 1 = also do vmb_adam's work for this stack (optimiser.step(); zero_grad(),
+                                       train.py:325-326) in the same call: hidden 32 runs it inside the step kernel
+                                       (the last CTA to finish an object reduces that object's gradient partials in a
+                                       fixed order and applies AdamW -- `grads` is then neither read nor written);
+                                       other hidden sizes launch the AdamW kernel behind the step.  `params` and `image`
+                                       are updated in place.  Needs backward = 1 and the fields below.               */
   void* k1_start_event;             /* optional cudaEvent_t recorded right before / after   */
   void* k1_stop_event;              /*   the fused K1 launch (roofline timing in bench.py)  */
+  /* ---- only read when fuse_adam = 1 (same meaning as in vmb_adam_args) ---------------- */
+  float* exp_avg;                   /* [B][stride] in/out                                   */
+  float* exp_avg_sq;                /* [B][stride] in/out                                   */
+  int*   step_counter;              /* optional DEVICE int[n_obj]: per-object step numbers  */
+  int    step;                      /* 1-based step number when step_counter == NULL        */
+  float  lr, beta1, beta2, eps, weight_decay;
+  int    guard_loss;                /* 1 = skip an object's update and raise the status bits if its loss explodes */
+  int*   status;                    /* optional device int[4], bits OR-ed in                */
 } vmb_step_args;
 
 int vmb_step(vmb_handle* h, const vmb_step_args* a, void* stream);
@@ -134,9 +148,10 @@ typedef struct vmb_adam_args {
   int*   status;            /* optional device int[4], bits OR-ed in                      */
   float lr, beta1, beta2, eps, weight_decay;
   int   zero_grads;
-  int*  step_counter;       /* optional DEVICE int: when set, t = *step_counter + 1 is used instead of
-                               `step` and the counter is incremented by the kernel, so that a captured
-                               CUDA graph of the step can be replayed                              */
+  int*  step_counter;       /* optional DEVICE int[n_obj]: when set, object b uses t = step_counter[b] + 1
+                               instead of `step` and the kernel increments every counter, so that a captured
+                               CUDA graph of the step can be replayed; per-object numbers let objects that
+                               joined the stack later keep a correct bias correction       */
 } vmb_adam_args;
 
 int vmb_adam(vmb_handle* h, const vmb_adam_args* a, void* stream);

@@ -227,6 +227,15 @@ class OracleEnsemble:
         return step_batch_loss(alpha, colour, batch["gt_depth"], batch["gt_colour"],
                                batch["sem"], batch["mask_depth"], batch["z"])
 
+    def loss_terms(self, batch) -> torch.Tensor:
+        """Per-object [B,4]: L_depth, L_colour, L_opacity and the weighted total (loss.py:57-60), what the kernels
+        write into ``loss_terms``."""
+        with torch.no_grad():
+            alpha, colour = self.forward(batch["pcs"])
+            l_d, l_c, l_o = batch_loss_terms(alpha, colour, batch["gt_depth"], batch["gt_colour"], batch["sem"],
+                                             batch["mask_depth"], batch["z"])
+            return torch.stack([l_d, l_c, l_o, l_d + 5.0 * l_c + 10.0 * l_o], dim=1)
+
     def grads(self, batch):
         self.opt.zero_grad(set_to_none=True)
         loss = self.loss(batch)

@@ -1,6 +1,5 @@
 """Parity at the shapes BASELINE.json names (configs[0..4]); configs[1] is the bench workload and is
-covered in test_umma_gpu.py.  Sizes the oracle cannot finish quickly are checked against the fp32
-CUDA kernel (itself oracle/golden-checked) and through size-independent properties."""
+covered in test_umma_gpu.py.  The reference is the CPU oracle at the full shape (a few seconds per case)."""
 import pytest
 import torch
 
@@ -29,30 +28,36 @@ def test_cfg0_imap_single_mlp_h256_100rays(impl):
 
 
 @pytest.mark.parametrize("n_obj", [50, 160])
-def test_cfg2_cfg3_many_objects_umma_vs_fp32_kernel(n_obj):
-    """configs[2] (50 objects) and configs[3] (160 objects = 8 x 20): every CTA walks several objects."""
+def test_cfg2_cfg3_many_objects_umma_vs_oracle(n_obj):
+    """configs[2] (50 objects x 1200 rays) and configs[3] (160 objects = 8 x 20): every CTA walks several objects.
+    Reference = the CPU oracle at the full shape."""
     R, S = 1200 if n_obj == 50 else 240, 10
     params = vo.init_params(n_obj, 32, seed=2)
-    db = to_dev(vo.synthetic_batch(n_obj, R, S, seed=3))
-    a = make_ensemble(params, 2.0, 32, impl="fp32")
+    batch = vo.synthetic_batch(n_obj, R, S, seed=3)
+    db = to_dev(batch)
+    orc = vo.OracleEnsemble(params, 2.0)
+    d_a, _, c_a, o_a = orc.render(batch)
+    _, g_ref = orc.grads(batch)
+    lt_ref = orc.loss_terms(batch).cuda()                      # [B,4] per-object terms
     u = make_ensemble(params, 2.0, 32, impl="umma")
-    d_a, _, c_a, o_a = a.render(db)
     d_u, _, c_u, o_u = u.render(db)
     assert rel_l2(d_u, d_a) < 1e-3 and rel_l2(c_u, c_a) < 1e-3 and rel_l2(o_u, o_a) < 1e-3
-    a.forward_backward(db); u.forward_backward(db)
+    u.forward_backward(db)
     # per-object losses agree object by object (no cross-object leakage when CTAs straddle objects)
-    lt = float(((a.loss_terms - u.loss_terms).abs() / (a.loss_terms.abs() + 1e-6)).max())
+    lt = float(((lt_ref - u.loss_terms).abs() / (lt_ref.abs() + 1e-6)).max())
     print('max per-object loss-term rel diff', lt)
     assert lt < 3e-2
     for k in vo.ALL_KEYS:
-        ga, gu = a.view(k, a.grads), u.view(k, u.grads)
+        ga, gu = g_ref[k].cuda(), u.view(k, u.grads)
         per_obj = ((ga - gu).flatten(1).norm(dim=1) / (ga.flatten(1).norm(dim=1) + 1e-20))
         # The losses are L1: d|x|/dx = sign(x) flips for rays whose residual is within the fp16 forward noise,
         # so a few objects with few contributing rays show large relative differences (deterministic, see
-        # tools/diag160.py); the bulk must agree closely.
+        # tools/diag160.py); the bulk must agree closely and the whole-stack gradient within the kernel's bar.
         q90 = float(per_obj.kthvalue(max(1, int(0.9 * n_obj))).values)
-        print(k, 'per-object grad rel-L2: median', float(per_obj.median()), 'p90', q90, 'max', float(per_obj.max()))
+        print(k, 'per-object grad rel-L2: median', float(per_obj.median()), 'p90', q90, 'max', float(per_obj.max()),
+              'stack', rel_l2(gu, ga))
         assert float(per_obj.median()) < 3e-2 and q90 < 0.1 and float(per_obj.max()) < 0.6, (k, float(per_obj.max()))
+        assert rel_l2(gu, ga) < 6e-2, k
     # independence: permuting the objects permutes the results
     perm = torch.randperm(n_obj, generator=torch.Generator().manual_seed(0))
     pp = {k: v[perm] for k, v in params.items()}

@@ -74,9 +74,11 @@ def _worker(rank, world, port, ret):
     local = {k: v[:, lo:hi].contiguous() for k, v in full.items()}
     ens = OracleBackedEnsemble(params, 2.0)
     stepper = ReplicatedStep(ens)
-    losses = [float(stepper.step(local)) for _ in range(3)]
+    # the next step's mask counts ride on this step's packed all-reduce: 1 counts collective up front, then ONE per step
+    losses = [float(stepper.step(local, next_batch=local)) for _ in range(3)]
     if rank == 0:
         ret["losses"] = losses
+        ret["collectives"] = stepper.collectives
         ret["w"] = ens.orc.params["mid1.0.0.weight"].detach().clone()
     dist.destroy_process_group()
 
@@ -93,6 +95,7 @@ def test_ray_sharded_replicated_step_equals_single_process():
     ref = vo.OracleEnsemble(params, 2.0)
     ref_losses = [float(ref.step(full)) for _ in range(3)]
     assert ret["losses"] == pytest.approx(ref_losses, rel=1e-4)
+    assert ret["collectives"] == 1 + 3
     w = ret["w"]
     err = float((w - ref.params["mid1.0.0.weight"].detach()).norm() / ref.params["mid1.0.0.weight"].norm())
     assert err < 1e-5

@@ -64,7 +64,7 @@ def test_frame_graph_matches_eager_loop(use_store):
             losses.append(l.clone()); draws.append(fl.out["pcs"].clone())
         torch.cuda.synchronize()
         ens.check_status()
-        assert int(fl.counter) == 7 + 3 and ens.step_count == 3 * n_iter and int(ens.step_counter) == 3 * n_iter
+        assert int(fl.counter) == 7 + 3 and ens.step_count == 3 * n_iter and int(ens.step_counter[0]) == 3 * n_iter
         results.append((torch.stack(losses).cpu(), draws, ens.params.clone()))
     (l_e, d_e, p_e), (l_g, d_g, p_g) = results
     # the frame loop's first draw == a plain sampler call with the same seed / offset, for EVERY object

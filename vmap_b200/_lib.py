@@ -36,8 +36,11 @@ class StepArgs(C.Structure):
         ("r_depth", _vp), ("r_var", _vp), ("r_colour", _vp), ("r_opacity", _vp),
         ("counts", _vp),
         ("colour_scaling", C.c_float), ("opacity_scaling", C.c_float),
-        ("backward", C.c_int), ("reserved", C.c_int),
+        ("backward", C.c_int), ("fuse_adam", C.c_int),
         ("k1_start_event", _vp), ("k1_stop_event", _vp),
+        ("exp_avg", _vp), ("exp_avg_sq", _vp), ("step_counter", _vp), ("step", C.c_int),
+        ("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float),
+        ("weight_decay", C.c_float), ("guard_loss", C.c_int), ("status", _vp),
     ]
 
 

@@ -20,15 +20,15 @@ struct AdamParams {
   float bc2_sqrt;             // sqrt(1 - b2^t)
   float eps;
   int zero_grads;
-  // optional device-resident step counter (CUDA-graph replay): t = *step_counter + 1 is read by
-  // every block on entry; the last block to finish publishes it and resets the ticket.
+  // optional device-resident per-object step numbers (CUDA-graph replay): t_b = step_counter[b] + 1 is read by
+  // every block on entry; the last block to finish increments them all and resets the ticket.
   int* step_counter; unsigned int* ticket;
   double lr, b1, b2d;
 };
 
 __global__ void __launch_bounds__(256) k_adamw(AdamParams a) {
   __shared__ int s_skip;
-  __shared__ float s_step_size, s_bc2_sqrt;
+  __shared__ float s_step_size[2], s_bc2_sqrt[2];
   // issue this thread's loads first: their latency overlaps the (serial, double-precision) bias-correction prologue
   const long long i4 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
   float4 p = make_float4(0.f, 0.f, 0.f, 0.f), g = p, m = p, v = p;
@@ -38,18 +38,20 @@ __global__ void __launch_bounds__(256) k_adamw(AdamParams a) {
     m = *reinterpret_cast<const float4*>(a.m + i4);
     v = *reinterpret_cast<const float4*>(a.v + i4);
   }
-  if (threadIdx.x == 0) {
-    s_skip = 0;
-    if (a.step_counter) {
-      const double t = (double)(*a.step_counter + 1);
-      s_step_size = (float)(a.lr / (1.0 - pow(a.b1, t)));
-      s_bc2_sqrt = (float)sqrt(1.0 - pow(a.b2d, t));
+  // a block covers 1024 consecutive floats = at most two rows (row pitch >= 1024): per-object step numbers
+  const int row0 = (int)(((long long)blockIdx.x * blockDim.x * 4) / a.stride);
+  if (threadIdx.x == 0) s_skip = 0;
+  if (threadIdx.x < 2) {
+    const int rb = row0 + threadIdx.x;
+    if (a.step_counter && rb < a.B) {
+      const double t = (double)(a.step_counter[rb] + 1);
+      s_step_size[threadIdx.x] = (float)(a.lr / (1.0 - pow(a.b1, t)));
+      s_bc2_sqrt[threadIdx.x] = (float)sqrt(1.0 - pow(a.b2d, t));
     } else {
-      s_step_size = a.step_size; s_bc2_sqrt = a.bc2_sqrt;
+      s_step_size[threadIdx.x] = a.step_size; s_bc2_sqrt[threadIdx.x] = a.bc2_sqrt;
     }
   }
   __syncthreads();
-  const float step_size = s_step_size, bc2_sqrt = s_bc2_sqrt;
   if (a.loss_terms) {       // render_rays.py:88-90: the reference aborts before the update
     int bad = 0;
     for (int i = threadIdx.x; i < a.B * 4; i += blockDim.x) {
@@ -60,11 +62,15 @@ __global__ void __launch_bounds__(256) k_adamw(AdamParams a) {
     if (bad) atomicOr(&s_skip, bad);
     __syncthreads();
     if (s_skip) {
+      // no update; the exploded gradients must not leak into the next step's accumulation
+      if (a.zero_grads && i4 < a.n) *reinterpret_cast<float4*>(a.g + i4) = make_float4(0.f, 0.f, 0.f, 0.f);
       if (blockIdx.x == 0 && threadIdx.x == 0 && a.status) atomicOr(a.status, s_skip);
       return;
     }
   }
   if (i4 < a.n) {
+  const int b = (int)(i4 / a.stride);
+  const float step_size = s_step_size[b - row0], bc2_sqrt = s_bc2_sqrt[b - row0];
   float* pp = &p.x; float* gg = &g.x; float* mm = &m.x; float* vv = &v.x;
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
@@ -80,7 +86,6 @@ __global__ void __launch_bounds__(256) k_adamw(AdamParams a) {
   *reinterpret_cast<float4*>(a.v + i4) = v;
   if (a.zero_grads) *reinterpret_cast<float4*>(a.g + i4) = make_float4(0.f, 0.f, 0.f, 0.f);
   if (a.image) {
-    const int b = (int)(i4 / a.stride);
     const int e = (int)(i4 - (long long)b * a.stride);
     __half* img = a.image + (size_t)b * a.img_halves;
 #pragma unroll
@@ -94,10 +99,16 @@ __global__ void __launch_bounds__(256) k_adamw(AdamParams a) {
   }
   }
   if (a.step_counter) {
+    __shared__ int s_last;
     __syncthreads();
     if (threadIdx.x == 0) {
       __threadfence();
-      if (atomicAdd(a.ticket, 1u) == gridDim.x - 1) { *a.step_counter += 1; *a.ticket = 0u; }
+      s_last = (atomicAdd(a.ticket, 1u) == gridDim.x - 1) ? 1 : 0;
+    }
+    __syncthreads();
+    if (s_last) {           // every block has read its step numbers: the last one to finish publishes t + 1
+      for (int i = threadIdx.x; i < a.B; i += blockDim.x) a.step_counter[i] += 1;
+      if (threadIdx.x == 0) *a.ticket = 0u;
     }
   }
 }

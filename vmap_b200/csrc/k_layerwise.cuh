@@ -54,8 +54,15 @@ struct Workspace {
     for (void* q : ptrs) if (q) cudaFree(q);
     *this = Workspace();
   }
-  cudaError_t ensure(long long P, int H_) {
-    if (P <= cap_points && H_ == H) return cudaSuccess;
+  bool in_graph = false;       // a captured CUDA graph holds these pointers: the buffers must never move again
+  // Grow-only.  Never reallocates while the stream is capturing or after a capture has baked the pointers
+  // into a graph (kernel arguments and TMA tensor maps): that would be a use-after-free at the next replay.
+  cudaError_t ensure(long long P, int H_, cudaStream_t st) {
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(st, &cs);
+    const bool capturing = cs != cudaStreamCaptureStatusNone;
+    if (P <= cap_points && H_ == H) { in_graph |= capturing; return cudaSuccess; }
+    if (capturing || in_graph) return cudaErrorStreamCaptureUnsupported;
     release();
     const long long Pp = (P + 127) / 128 * 128;
     cudaError_t e = cudaSuccess;
@@ -500,7 +507,7 @@ constexpr long long FWD_CHUNK = 1LL << 18;
 static int launch_forward(Workspace& ws, const VmbLayout& L, const StepParams& sp, const void* image, cudaStream_t st, std::string& err) {
   if (!get_encode()) { err = "cuTensorMapEncodeTiled not available from the driver"; return -2; }
   const long long N = sp.R;
-  LW_TRY(ws.ensure(std::min(N, FWD_CHUNK), L.H));
+  LW_TRY(ws.ensure(std::min(N, FWD_CHUNK), L.H, st));
   for (int b = 0; b < sp.B; ++b)
     for (long long p0 = 0; p0 < N; p0 += FWD_CHUNK) {
       const long long n = std::min(FWD_CHUNK, N - p0);
@@ -519,7 +526,7 @@ static int launch_forward(Workspace& ws, const VmbLayout& L, const StepParams& s
 static int launch_step(Workspace& ws, const VmbLayout& L, const StepParams& sp, const void* image, cudaStream_t st, std::string& err) {
   if (!get_encode()) { err = "cuTensorMapEncodeTiled not available from the driver"; return -2; }
   if (sp.S > 32) { err = "layer-wise path: n_samples > 32"; return -4; }
-  LW_TRY(ws.ensure((long long)sp.R * sp.S, L.H));
+  LW_TRY(ws.ensure((long long)sp.R * sp.S, L.H, st));
   for (int b = 0; b < sp.B; ++b) {
     int rc;
     switch (L.H) {

@@ -13,6 +13,7 @@
 #include "k_sampler.cuh"
 #include "k_ingest.cuh"
 #include "k_step_umma.cuh"
+#include "k_step_fused.cuh"
 #include "k_gemm_umma.cuh"
 #include "k_layerwise.cuh"
 
@@ -24,10 +25,13 @@ struct vmb_handle {
   int* d_img_index;       // [P] param index -> half index inside the fp16 image (or -1)
   unsigned int* d_ticket; // last-block ticket of the fused AdamW (device step counter mode)
   unsigned int* d_smax;   // [max_obj] sampler: per-object max sampled depth (order-preserving key)
+  float* d_partials;      // fused step: [(max_obj + n_sm)][stride] per-(CTA, object) gradient partials (allocated on first use)
+  unsigned int* d_objdone;// fused step: [max_obj] finished-segment counters (self-resetting)
   int img_halves;
   bool umma_ok;           // hidden 32: fused tcgen05 kernel + its pre-swizzled fp16 image
   bool lw_ok;             // hidden 64/128/256: layer-wise tcgen05 GEMM path + row-major fp16 image
-  lw::Workspace ws;
+  lw::Workspace ws;       // training-step activations (may be baked into a captured graph)
+  lw::Workspace ws_fwd;   // forward-only queries (vmb_forward): separate, so eval_points never moves the step's buffers
   std::string err;
 };
 
@@ -116,7 +120,7 @@ int vmb_create(vmb_handle** out, int device, int max_obj, int hidden, int n_freq
   h->n_sm = 148;
   cudaDeviceGetAttribute(&h->n_sm, cudaDevAttrMultiProcessorCount, device);
   h->L = vmb_make_layout(hidden, n_freq);
-  h->d_counts = nullptr; h->d_img_index = nullptr; h->d_ticket = nullptr; h->d_smax = nullptr; h->img_halves = 0; h->umma_ok = false; h->lw_ok = false;
+  h->d_counts = nullptr; h->d_img_index = nullptr; h->d_ticket = nullptr; h->d_smax = nullptr; h->d_partials = nullptr; h->d_objdone = nullptr; h->img_halves = 0; h->umma_ok = false; h->lw_ok = false;
   cudaError_t e = cudaMalloc(&h->d_counts, sizeof(int) * 4 * max_obj);
   if (e == cudaSuccess) e = cudaMalloc(&h->d_ticket, sizeof(unsigned int));
   if (e == cudaSuccess) e = cudaMemset(h->d_ticket, 0, sizeof(unsigned int));
@@ -150,7 +154,10 @@ void vmb_destroy(vmb_handle* h) {
   if (h->d_img_index) cudaFree(h->d_img_index);
   if (h->d_ticket) cudaFree(h->d_ticket);
   if (h->d_smax) cudaFree(h->d_smax);
+  if (h->d_partials) cudaFree(h->d_partials);
+  if (h->d_objdone) cudaFree(h->d_objdone);
   h->ws.release();
+  h->ws_fwd.release();
   delete h;
 }
 
@@ -164,25 +171,78 @@ int vmb_mask_counts(vmb_handle* h, int n_obj, int n_rays, const unsigned char* s
   return VMB_OK;
 }
 
+// scalars exactly as torch.optim.adamw._single_tensor_adamw forms them (python doubles)
+struct AdamScalars { float lr_wd, one_m_b1, b2, one_m_b2, step_size, bc2_sqrt; double lr, b1, b2d; };
+static AdamScalars adam_scalars(float lr_f, float b1_f, float b2_f, float wd_f, int step) {
+  AdamScalars q;
+  const double lr = lr_f, b1 = b1_f, b2 = b2_f;
+  q.lr = lr; q.b1 = b1; q.b2d = b2;
+  q.lr_wd = (float)(1.0 - lr * (double)wd_f);
+  q.one_m_b1 = (float)(1.0 - b1);
+  q.b2 = (float)b2;
+  q.one_m_b2 = (float)(1.0 - b2);
+  const double t = (double)(step < 1 ? 1 : step);
+  q.step_size = (float)(lr / (1.0 - std::pow(b1, t)));
+  q.bc2_sqrt = (float)std::sqrt(1.0 - std::pow(b2, t));
+  return q;
+}
+
+// scratch of the fused step kernel (gradient partial rows + per-object arrival counters): allocated on first use,
+// never while a stream capture is in progress (a captured graph bakes the pointers in)
+static int fused_scratch(vmb_handle* h, cudaStream_t st) {
+  if (h->d_partials) return VMB_OK;
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  cudaStreamIsCapturing(st, &cs);
+  if (cs != cudaStreamCaptureStatusNone)
+    return fail(h, VMB_E_CUDA, "vmb_step: first fused step of a handle must run outside stream capture (scratch allocation)");
+  const size_t rows = (size_t)fused_rows_needed(h->max_obj, h->n_sm);
+  cudaError_t e = cudaMalloc(&h->d_partials, rows * h->L.stride * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc(&h->d_objdone, sizeof(unsigned int) * (size_t)h->max_obj);
+  if (e == cudaSuccess) e = cudaMemset(h->d_objdone, 0, sizeof(unsigned int) * (size_t)h->max_obj);
+  if (e != cudaSuccess) return fail(h, VMB_E_NOMEM, cudaGetErrorString(e));
+  return VMB_OK;
+}
+
+static bool use_v6_kernel() {      // VMB_K1=v6: the round-1 kernel chain (K0 + k_step_umma + atomics + K2), kept for A/B timing
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("VMB_K1"); v = (e && !strcmp(e, "v6")) ? 1 : 0; }
+  return v == 1;
+}
+
+static int launch_adamw(vmb_handle* h, int n_obj, float* params, float* grads, float* m, float* v, void* image,
+                        const float* loss_terms, int* status, const AdamScalars& q, float eps, int zero_grads,
+                        int* step_counter, cudaStream_t st) {
+  if (h->L.stride < 1024) return fail(h, VMB_E_UNSUPPORTED, "vmb_adam: row pitch below one block");
+  AdamParams p;
+  memset(&p, 0, sizeof(p));
+  p.n = (long long)n_obj * h->L.stride; p.stride = h->L.stride; p.P = h->L.P; p.B = n_obj;
+  p.p = params; p.g = grads; p.m = m; p.v = v;
+  p.image = (__half*)image; p.img_index = h->d_img_index; p.img_halves = h->img_halves;
+  p.loss_terms = loss_terms; p.status = status;
+  p.lr_wd = q.lr_wd; p.one_m_b1 = q.one_m_b1; p.b2 = q.b2; p.one_m_b2 = q.one_m_b2;
+  p.step_counter = step_counter; p.ticket = h->d_ticket; p.lr = q.lr; p.b1 = q.b1; p.b2d = q.b2d;
+  p.step_size = q.step_size; p.bc2_sqrt = q.bc2_sqrt;
+  p.eps = eps;
+  p.zero_grads = zero_grads;
+  const long long n4 = p.n / 4;
+  const int blocks = (int)((n4 + 255) / 256);
+  k_adamw<<<blocks, 256, 0, st>>>(p);
+  CUDA_TRY(h, cudaGetLastError());
+  return VMB_OK;
+}
+
 int vmb_step(vmb_handle* h, const vmb_step_args* a, void* stream) {
   if (!h || !a) return fail(h, VMB_E_ARG, "vmb_step: null argument");
   if (a->n_obj <= 0 || a->n_obj > h->max_obj || a->n_rays <= 0 || a->n_samples <= 0 || a->n_samples > 32)
     return fail(h, VMB_E_ARG, "vmb_step: bad n_obj / n_rays / n_samples (1 <= S <= 32)");
   if (!a->pcs || !a->z_vals || !a->gt_depth || !a->gt_colour || !a->sem || !a->mask_depth || !a->params ||
-      !a->scale || !a->loss_terms || (a->backward && !a->grads))
+      !a->scale || !a->loss_terms || (a->backward && !a->grads && !a->fuse_adam))
     return fail(h, VMB_E_ARG, "vmb_step: missing tensor pointer");
+  if (a->fuse_adam && (!a->backward || !a->exp_avg || !a->exp_avg_sq || (a->step < 1 && !a->step_counter)))
+    return fail(h, VMB_E_ARG, "vmb_step: fuse_adam needs backward = 1, exp_avg / exp_avg_sq and a step number");
   cudaStream_t st = (cudaStream_t)stream;
-  const int* counts = a->counts;
-  if (!counts) {
-    k_mask_counts<<<a->n_obj, 256, 0, st>>>(a->n_rays, a->sem, a->sem_stride, a->mask_depth, a->mask_stride,
-                                            h->d_counts, a->loss_terms);
-    CUDA_TRY(h, cudaGetLastError());
-    counts = h->d_counts;
-  } else {
-    CUDA_TRY(h, cudaMemsetAsync(a->loss_terms, 0, sizeof(float) * 4 * a->n_obj, st));
-  }
   int impl = a->impl;
-  const bool umma_possible = h->umma_ok && a->image != nullptr && a->n_samples <= UMMA_MAX_S;
+  const bool umma_possible = h->umma_ok && a->image != nullptr;
   const bool lw_possible = h->lw_ok && a->image != nullptr;
   if (impl == VMB_IMPL_AUTO) impl = umma_possible ? VMB_IMPL_UMMA : (lw_possible ? VMB_IMPL_LAYERWISE : VMB_IMPL_FP32);
   StepParams sp;
@@ -196,28 +256,79 @@ int vmb_step(vmb_handle* h, const vmb_step_args* a, void* stream) {
   sp.mask = a->mask_depth; sp.mask_stride = a->mask_stride;
   sp.params = a->params; sp.scale = a->scale; sp.grads = a->grads; sp.loss_terms = a->loss_terms;
   sp.r_depth = a->r_depth; sp.r_var = a->r_var; sp.r_colour = a->r_colour; sp.r_opacity = a->r_opacity;
-  sp.counts = counts; sp.cs = a->colour_scaling; sp.os = a->opacity_scaling; sp.backward = a->backward;
+  sp.cs = a->colour_scaling; sp.os = a->opacity_scaling; sp.backward = a->backward;
+  AdamScalars q;
+  memset(&q, 0, sizeof(q));
+  if (a->fuse_adam) q = adam_scalars(a->lr, a->beta1, a->beta2, a->weight_decay, a->step);
   struct EvGuard {      // records the optional K1 timing events around whichever kernel runs
     cudaEvent_t stop; cudaStream_t st;
     ~EvGuard() { if (stop) cudaEventRecord(stop, st); }
-  } evg{(cudaEvent_t)a->k1_stop_event, st};
-  if (a->k1_start_event) cudaEventRecord((cudaEvent_t)a->k1_start_event, st);
-  if (impl == VMB_IMPL_UMMA) {
-    if (!umma_possible) return fail(h, VMB_E_UNSUPPORTED, "vmb_step: UMMA path needs hidden=32, n_freq=6, an image and S<=16");
+  };
+
+  // ---- hidden 32: ONE launch (counts + step + ordered gradient reduction (+ AdamW)) ----------------------------
+  if (impl == VMB_IMPL_UMMA && !use_v6_kernel()) {
+    if (!umma_possible) return fail(h, VMB_E_UNSUPPORTED, "vmb_step: tensor-core path needs hidden=32, n_freq=6 and an image");
+    const int rc0 = fused_scratch(h, st);
+    if (rc0 != VMB_OK) return rc0;
+    FusedExtra fx;
+    memset(&fx, 0, sizeof(fx));
+    fx.partials = h->d_partials; fx.obj_done = h->d_objdone; fx.counts_in = a->counts;
+    fx.fuse_adam = a->fuse_adam ? 1 : 0;
+    if (a->fuse_adam) {
+      fx.p = const_cast<float*>(a->params); fx.m = a->exp_avg; fx.v = a->exp_avg_sq;
+      fx.image_out = (__half*)const_cast<void*>(a->image); fx.img_index = h->d_img_index; fx.img_halves = h->img_halves;
+      fx.step_counter = a->step_counter; fx.step_size = q.step_size; fx.bc2_sqrt = q.bc2_sqrt;
+      fx.lr = q.lr; fx.b1d = q.b1; fx.b2d = q.b2d;
+      fx.lr_wd = q.lr_wd; fx.one_m_b1 = q.one_m_b1; fx.b2 = q.b2; fx.one_m_b2 = q.one_m_b2; fx.eps = a->eps;
+      fx.guard_loss = a->guard_loss; fx.status = a->status;
+    }
+    EvGuard evg{(cudaEvent_t)a->k1_stop_event, st};
+    if (a->k1_start_event) cudaEventRecord((cudaEvent_t)a->k1_start_event, st);
     std::string err;
-    const int rc = umma_launch_step(h->L, sp, a->image, st, err);
+    const int rc = fused_launch_step(h->L, sp, fx, a->image, h->n_sm, st, err);
     if (rc != VMB_OK) return fail(h, rc, err);
     return VMB_OK;
   }
-  if (impl == VMB_IMPL_LAYERWISE) {
-    if (!lw_possible) return fail(h, VMB_E_UNSUPPORTED, "vmb_step: layer-wise path needs hidden 64/128/256, n_freq=6 and an image");
-    std::string err;
-    const int rc = lw::launch_step(h->ws, h->L, sp, a->image, st, err);
-    if (rc != VMB_OK) return fail(h, rc, err);
-    return VMB_OK;
+
+  // ---- other paths: K0 (mask counts) -> K1 -> [K2] ---------------------------------------------------------------
+  const int* counts = a->counts;
+  if (!counts) {
+    k_mask_counts<<<a->n_obj, 256, 0, st>>>(a->n_rays, a->sem, a->sem_stride, a->mask_depth, a->mask_stride,
+                                            h->d_counts, a->loss_terms);
+    CUDA_TRY(h, cudaGetLastError());
+    counts = h->d_counts;
+  } else {
+    CUDA_TRY(h, cudaMemsetAsync(a->loss_terms, 0, sizeof(float) * 4 * a->n_obj, st));
   }
-  if (impl != VMB_IMPL_FP32) return fail(h, VMB_E_ARG, "vmb_step: unknown impl");
-  return dispatch_fp32(h, sp, st);
+  sp.counts = counts;
+  if (a->backward && !a->grads) return fail(h, VMB_E_ARG, "vmb_step: this path needs the grads block");
+  int rc = VMB_OK;
+  {
+    EvGuard evg{(cudaEvent_t)a->k1_stop_event, st};
+    if (a->k1_start_event) cudaEventRecord((cudaEvent_t)a->k1_start_event, st);
+    if (impl == VMB_IMPL_UMMA) {
+      if (!umma_possible || a->n_samples > UMMA_MAX_S)
+        return fail(h, VMB_E_UNSUPPORTED, "vmb_step: round-1 UMMA kernel needs hidden=32, n_freq=6, an image and S<=16");
+      std::string err;
+      rc = umma_launch_step(h->L, sp, a->image, st, err);
+      if (rc != VMB_OK) return fail(h, rc, err);
+    } else if (impl == VMB_IMPL_LAYERWISE) {
+      if (!lw_possible) return fail(h, VMB_E_UNSUPPORTED, "vmb_step: layer-wise path needs hidden 64/128/256, n_freq=6 and an image");
+      std::string err;
+      rc = lw::launch_step(h->ws, h->L, sp, a->image, st, err);
+      if (rc != VMB_OK) return fail(h, rc, err);
+    } else if (impl == VMB_IMPL_FP32) {
+      rc = dispatch_fp32(h, sp, st);
+      if (rc != VMB_OK) return rc;
+    } else {
+      return fail(h, VMB_E_ARG, "vmb_step: unknown impl");
+    }
+  }
+  if (a->fuse_adam)
+    return launch_adamw(h, a->n_obj, const_cast<float*>(a->params), a->grads, a->exp_avg, a->exp_avg_sq,
+                        (h->umma_ok || h->lw_ok) ? const_cast<void*>(a->image) : nullptr,
+                        a->guard_loss ? a->loss_terms : nullptr, a->status, q, a->eps, 1, a->step_counter, st);
+  return VMB_OK;
 }
 
 int vmb_forward(vmb_handle* h, const vmb_forward_args* a, void* stream) {
@@ -235,13 +346,16 @@ int vmb_forward(vmb_handle* h, const vmb_forward_args* a, void* stream) {
   sp.out_colour = a->colour; sp.colour_stride = a->colour_stride;
   if (a->image && h->umma_ok) {
     std::string err;
-    const int rc = umma_launch_step(h->L, sp, a->image, (cudaStream_t)stream, err);
+    FusedExtra fx;
+    memset(&fx, 0, sizeof(fx));
+    const int rc = use_v6_kernel() ? umma_launch_step(h->L, sp, a->image, (cudaStream_t)stream, err)
+                                   : fused_launch_step(h->L, sp, fx, a->image, h->n_sm, (cudaStream_t)stream, err);
     if (rc) return fail(h, rc == -4 ? VMB_E_UNSUPPORTED : VMB_E_CUDA, err);
     return VMB_OK;
   }
   if (a->image && h->lw_ok) {
     std::string err;
-    const int rc = lw::launch_forward(h->ws, h->L, sp, a->image, (cudaStream_t)stream, err);
+    const int rc = lw::launch_forward(h->ws_fwd, h->L, sp, a->image, (cudaStream_t)stream, err);
     if (rc) return fail(h, rc == -4 ? VMB_E_UNSUPPORTED : VMB_E_CUDA, err);
     return VMB_OK;
   }
@@ -253,31 +367,9 @@ int vmb_adam(vmb_handle* h, const vmb_adam_args* a, void* stream) {
       !a->exp_avg || !a->exp_avg_sq)
     return fail(h, VMB_E_ARG, "vmb_adam: bad arguments");
   if (a->image && !h->umma_ok && !h->lw_ok) return fail(h, VMB_E_UNSUPPORTED, "vmb_adam: no fp16 image for this hidden size");
-  AdamParams p;
-  memset(&p, 0, sizeof(p));
-  p.n = (long long)a->n_obj * h->L.stride; p.stride = h->L.stride; p.P = h->L.P; p.B = a->n_obj;
-  p.p = a->params; p.g = a->grads; p.m = a->exp_avg; p.v = a->exp_avg_sq;
-  p.image = (__half*)a->image; p.img_index = h->d_img_index; p.img_halves = h->img_halves;
-  p.loss_terms = a->loss_terms; p.status = a->status;
-  // scalars exactly as torch.optim.adamw._single_tensor_adamw forms them (python doubles)
-  const double lr = a->lr, b1 = a->beta1, b2 = a->beta2;
-  p.lr_wd = (float)(1.0 - lr * (double)a->weight_decay);
-  p.one_m_b1 = (float)(1.0 - b1);
-  p.b2 = (float)b2;
-  p.one_m_b2 = (float)(1.0 - b2);
-  const double tstep = (double)(a->step < 1 ? 1 : a->step);
-  const double bc1 = 1.0 - std::pow(b1, tstep);
-  const double bc2 = 1.0 - std::pow(b2, tstep);
-  p.step_counter = a->step_counter; p.ticket = h->d_ticket; p.lr = lr; p.b1 = b1; p.b2d = b2;
-  p.step_size = (float)(lr / bc1);
-  p.bc2_sqrt = (float)std::sqrt(bc2);
-  p.eps = a->eps;
-  p.zero_grads = a->zero_grads;
-  const long long n4 = p.n / 4;
-  const int blocks = (int)((n4 + 255) / 256);
-  k_adamw<<<blocks, 256, 0, (cudaStream_t)stream>>>(p);
-  CUDA_TRY(h, cudaGetLastError());
-  return VMB_OK;
+  const AdamScalars q = adam_scalars(a->lr, a->beta1, a->beta2, a->weight_decay, a->step);
+  return launch_adamw(h, a->n_obj, a->params, a->grads, a->exp_avg, a->exp_avg_sq, a->image, a->loss_terms, a->status, q,
+                      a->eps, a->zero_grads, a->step_counter, (cudaStream_t)stream);
 }
 
 int vmb_build_image(vmb_handle* h, int n_obj, const float* params, void* image, void* stream) {

@@ -4,8 +4,9 @@ One ``VmapEnsemble`` owns, for a stack of ``n_obj`` object MLPs on one GPU:
 ``params | grads | exp_avg | exp_avg_sq`` as ``[n_obj, stride]`` fp32 blocks, the fp16
 tensor-core weight image, per-object scales, loss terms and the status word.  It replaces
 what ``utils.update_vmap`` + ``torch.optim.AdamW`` hold in the reference
-(utils.py:30-34, train.py:67) and runs train.py:293-326 as three kernel launches
-(mask counts, fused forward+loss+backward, fused AdamW).
+(utils.py:30-34, train.py:67) and runs train.py:293-326 as ONE kernel launch at hidden 32 (mask counts, fused
+forward+loss+backward, ordered gradient reduction and AdamW all inside ``vmb_step(fuse_adam=1)``); wide models
+(hidden 64/128/256) run mask counts + the layer-wise step + the AdamW kernel behind the same call.
 """
 from __future__ import annotations
 
@@ -67,7 +68,9 @@ class VmapEnsemble:
         self.loss_terms = torch.zeros(n_obj, 4, **f32)
         self.status = torch.zeros(4, dtype=torch.int32, device=dev)
         self.step_count = 0
-        self.step_counter = torch.zeros(1, dtype=torch.int32, device=dev)   # device copy (graph replay)
+        # per-object step numbers on the device: graph replay needs them there, and objects that join a stack later
+        # (update_vmap(..., keep_optimizer_state=True)) keep their own bias correction
+        self.step_counter = torch.zeros(n_obj, dtype=torch.int32, device=dev)
 
     def __del__(self):
         try:
@@ -102,6 +105,11 @@ class VmapEnsemble:
         self.step_count = 0
         self.step_counter.zero_()
 
+    def reset_optimizer_row(self, row: int):
+        """Start AdamW from scratch for ONE object (a freshly loaded checkpoint, vmap.py:478-491)."""
+        self.exp_avg[row].zero_(); self.exp_avg_sq[row].zero_(); self.grads[row].zero_()
+        self.step_counter[row] = 0
+
     def refresh_image(self):
         if self.image is not None:
             with torch.cuda.device(self.device):
@@ -109,7 +117,8 @@ class VmapEnsemble:
                                                                   _ptr(self.image), _stream()), "vmb_build_image")
 
     # ---- kernels ----------------------------------------------------------------------------
-    def _step_args(self, batch, backward: bool, outputs=None, impl: Optional[str] = None, counts=None):
+    def _step_args(self, batch, backward: bool, outputs=None, impl: Optional[str] = None, counts=None,
+                   fuse_adam: bool = False, guard_loss: bool = True):
         pcs, z = batch["pcs"], batch["z"]
         B, R, S = pcs.shape[0], pcs.shape[1], pcs.shape[2]
         assert B == self.n_obj and pcs.shape[3] == 3 and tuple(z.shape) == (B, R, S)
@@ -137,13 +146,22 @@ class VmapEnsemble:
         a.counts = _ptr(counts)
         a.colour_scaling, a.opacity_scaling = self.colour_scaling, self.opacity_scaling
         a.backward = 1 if backward else 0
+        if fuse_adam:
+            a.fuse_adam = 1
+            a.exp_avg, a.exp_avg_sq = _ptr(self.exp_avg), _ptr(self.exp_avg_sq)
+            a.step_counter, a.step = _ptr(self.step_counter), 0
+            a.lr, a.beta1, a.beta2, a.eps = self.lr, self.betas[0], self.betas[1], self.eps
+            a.weight_decay = self.weight_decay
+            a.guard_loss, a.status = (1 if guard_loss else 0), _ptr(self.status)
         return a
 
     def forward_backward(self, batch, outputs=None, backward: bool = True, impl: Optional[str] = None,
-                         counts: Optional[torch.Tensor] = None, k1_events=None):
-        """K0 + K1: accumulates into ``self.grads`` and overwrites ``self.loss_terms``.
+                         counts: Optional[torch.Tensor] = None, k1_events=None, fuse_adam: bool = False,
+                         guard_loss: bool = True):
+        """K0 + K1: accumulates into ``self.grads`` and overwrites ``self.loss_terms``; with ``fuse_adam`` the
+        optimiser update happens in the same call (``self.grads`` untouched at hidden 32).
         ``k1_events`` = (start, stop) torch.cuda.Event pair recorded around the K1 launch."""
-        a = self._step_args(batch, backward, outputs, impl, counts)
+        a = self._step_args(batch, backward, outputs, impl, counts, fuse_adam, guard_loss)
         if k1_events is not None:
             for ev in k1_events:
                 if not ev.cuda_event:
@@ -182,21 +200,19 @@ class VmapEnsemble:
             _lib.check(self._handle, self.lib.vmb_adam(self._handle, C.byref(a), _stream()), "vmb_adam")
 
     def step(self, batch, impl: Optional[str] = None) -> torch.Tensor:
-        """One optimisation step (train.py:293-326). Returns the summed loss (device scalar)."""
-        self.forward_backward(batch, impl=impl)
-        self.adam_step()
+        """One optimisation step (train.py:293-326) in one library call. Returns the summed loss (device scalar)."""
+        self.forward_backward(batch, impl=impl, fuse_adam=True)
+        self.step_count += 1
         return self.loss_terms[:, 3].sum()
 
     def capture_step(self, batch, impl: Optional[str] = None) -> "torch.cuda.CUDAGraph":
-        """Capture K0+K1+K2 on ``batch``'s (fixed) buffers into a CUDA graph; refill the buffers
+        """Capture the step (one launch at hidden 32) on ``batch``'s (fixed) buffers into a CUDA graph; refill the buffers
         and ``replay()`` for every step.  Removes the per-launch host overhead of the loop."""
         self.forward_backward(batch, impl=impl, backward=False)      # warm-up: sets kernel attributes
         torch.cuda.synchronize(self.device)
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
-            self.forward_backward(batch, impl=impl)
-            self.adam_step()
-        self.step_count -= 1                                          # capture does not execute
+            self.forward_backward(batch, impl=impl, fuse_adam=True)
         self._graph_batch = batch
         return g
 
@@ -209,33 +225,72 @@ class VmapEnsemble:
         self.forward_backward(batch, outputs=out, backward=False, impl=impl)
         return out["depth"], out["var"], out["colour"], out["opacity"]
 
-    def eval_points(self, points: torch.Tensor, impl: Optional[str] = None):
-        """Forward only on raw points [B,N,3] -> alpha [B,N], colour [B,N,3] (trainer.py:77-90).
+    def eval_points(self, points: torch.Tensor, impl: Optional[str] = None, row: Optional[int] = None,
+                    chunk: int = 1 << 21):
+        """Forward only on raw points -> alpha (raw*10, model.py:77), colour (trainer.py:77-90).
+        ``row=None``: points [B,N,3], every object evaluates its own set -> alpha [B,N], colour [B,N,3].
+        ``row=r``: points [N,3] evaluated by object r ONLY (one-row views of the packed state are handed to
+        ``vmb_forward`` with n_obj = 1, so meshing one object of a 160-object stack costs one object's work)
+        -> alpha [N], colour [N,3].  ``chunk`` bounds the points per launch (the reference uses 100k chunks).
         ``impl="fp32"`` forces the CUDA-core kernel; otherwise hidden 32 runs the forward half of the fused
         tcgen05 kernel and hidden 64/128/256 the layer-wise tcgen05 GEMMs, on the fp16 weight image."""
-        B, N, _ = points.shape
-        assert B == self.n_obj and points.is_contiguous() and points.dtype == torch.float32
+        if row is None:
+            B, N, _ = points.shape
+            assert B == self.n_obj
+            params, scale, image = self.params, self.scale, self.image
+        else:
+            assert 0 <= row < self.n_obj and points.dim() == 2
+            B, N = 1, points.shape[0]
+            points = points[None]
+            params, scale = self.params[row:row + 1], self.scale[row:row + 1]
+            image = self.image[row:row + 1] if self.image is not None else None
+        assert points.is_contiguous() and points.dtype == torch.float32 and points.device == self.device
         alpha = torch.empty(B, N, dtype=torch.float32, device=self.device)
         colour = torch.empty(B, N, 3, dtype=torch.float32, device=self.device)
-        a = _lib.ForwardArgs()
-        a.n_obj, a.n_points = B, N
-        a.points, a.points_stride = _ptr(points), N * 3
-        a.params, a.scale = _ptr(self.params), _ptr(self.scale)
-        a.alpha, a.alpha_stride = _ptr(alpha), N
-        a.colour, a.colour_stride = _ptr(colour), N * 3
-        if (impl or self.impl) != "fp32" and self.image is not None:
-            a.image = _ptr(self.image)
+        use_image = (impl or self.impl) != "fp32" and image is not None
         with torch.cuda.device(self.device):
-            _lib.check(self._handle, self.lib.vmb_forward(self._handle, C.byref(a), _stream()), "vmb_forward")
+            for n0 in range(0, N, chunk):
+                n = min(chunk, N - n0)
+                a = _lib.ForwardArgs()
+                a.n_obj, a.n_points = B, n
+                a.points, a.points_stride = C.c_void_p(points.data_ptr() + n0 * 12), N * 3
+                a.params, a.scale = _ptr(params), _ptr(scale)
+                a.alpha, a.alpha_stride = C.c_void_p(alpha.data_ptr() + n0 * 4), N
+                a.colour, a.colour_stride = C.c_void_p(colour.data_ptr() + n0 * 12), N * 3
+                if use_image:
+                    a.image = _ptr(image)
+                _lib.check(self._handle, self.lib.vmb_forward(self._handle, C.byref(a), _stream()), "vmb_forward")
+        if row is not None:
+            return alpha[0], colour[0]
         return alpha, colour
 
-    def check_status(self):
-        """Host sync: raise if the device flagged a loss explosion / non-finite loss."""
-        st = int(self.status[0].item())
+    def poll_status(self):
+        """Asynchronous guard (no host sync): copy the device status word to pinned memory after this step's
+        work and raise if a copy enqueued by an EARLIER call has landed with a guard bit set.  The reference
+        exit(-1)s on a loss explosion (render_rays.py:88-90); here the device skips the update and training
+        stops with LossExplode at most one poll later.  Called by FusedAdamW.step and FrameLoop.run."""
+        if getattr(self, "_status_host", None) is None:
+            self._status_host = torch.zeros(4, dtype=torch.int32).pin_memory()
+            self._status_event = torch.cuda.Event()
+            self._status_pending = False
+        if self._status_pending and self._status_event.query():
+            self._raise_for(int(self._status_host[0]))
+        if torch.cuda.is_current_stream_capturing():
+            return
+        self._status_host.copy_(self.status, non_blocking=True)
+        self._status_event.record(torch.cuda.current_stream(self.device))
+        self._status_pending = True
+
+    @staticmethod
+    def _raise_for(st: int):
         if st & _lib.VMB_ST_LOSS_EXPLODE:
             raise LossExplode("loss explode (a per-object loss term exceeded 1e5); update skipped")
         if st & _lib.VMB_ST_NONFINITE:
             raise LossExplode("non-finite loss; update skipped")
+
+    def check_status(self):
+        """Host sync: raise if the device flagged a loss explosion / non-finite loss."""
+        self._raise_for(int(self.status[0].item()))
 
 
 class StepInputs:

@@ -3,10 +3,12 @@
 The reference's per-frame loop (train.py:195-326) is launch-bound at its shipped configuration (20 objects x 120
 rays per step: ~25 us of kernel work per step behind ~60 us of Python + launches).  ``FrameLoop`` captures
 
-    table upload (one small H2D from a pinned buffer) -> K3 pass 1 -> K3 pass 2 -> draw counter += 1
-      -> n_iter x [ K0 mask counts -> K1 fused step on the it-th ray slice -> K2 AdamW -> loss copy ]
+    K3 pass 1 -> K3 pass 2 -> draw counter += 1
+      -> n_iter x [ fused step on the it-th ray slice (+ AdamW) -> loss copy ]
 
-once, on persistent buffers, and replays it per frame.  What changes between frames lives in device memory (Adam
+once, on persistent buffers, and replays it per frame; the one small host->device copy of the per-frame tables is
+enqueued right before the replay (outside the graph, so the pinned source buffer is guarded by its own event and
+the host can fill the next frame's tables as soon as that copy -- not the whole frame -- has completed).  What changes between frames lives in device memory (Adam
 step counter, sampler draw counter) or in the pinned table buffer (keyframe slots / boxes / counts), so a replay
 draws fresh samples and continues the optimiser exactly as the eager loop would.
 """
@@ -46,9 +48,10 @@ class FrameLoop:
         self.tables.fill_store(kt)
 
     # ---- the frame -----------------------------------------------------------------------------------------
-    def _enqueue(self) -> None:
+    def _enqueue(self, upload: bool = True) -> None:
         s, R = self.smp, self.n_frames * self.n_pix // self.n_iter
-        self.tables.upload()
+        if upload:
+            self.tables.upload()
         if self.store is not None:
             s.sample_store(self.store, self.tables, self.n_frames, self.n_pix, self.rays_dir, seed=self.seed,
                            out=self.out, offset_dev=self.counter)
@@ -61,6 +64,7 @@ class FrameLoop:
 
     def run_eager(self) -> torch.Tensor:
         """The same frame without a graph (reference for tests / first frames)."""
+        self.ens.poll_status()
         self._enqueue()
         return self.losses
 
@@ -79,7 +83,7 @@ class FrameLoop:
         torch.cuda.synchronize(ens.device)
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
-            self._enqueue()
+            self._enqueue(upload=False)
         for dst, src in zip((ens.params, ens.grads, ens.exp_avg, ens.exp_avg_sq, ens.step_counter, self.counter), snap):
             dst.copy_(src)
         if img is not None:
@@ -90,6 +94,8 @@ class FrameLoop:
         """Replay the captured frame; returns the per-iteration summed losses (device tensor [n_iter])."""
         if self.graph is None:
             self.capture()
+        self.ens.poll_status()            # raises LossExplode if an earlier frame tripped the device guard
+        self.tables.upload()
         self.graph.replay()
         self.ens.step_count += self.n_iter
         return self.losses

@@ -23,6 +23,7 @@ class FusedAdamW:
         for ens in list(_DIRTY):
             ens.lr, ens.weight_decay = self.defaults["lr"], self.defaults["weight_decay"]
             ens.betas, ens.eps = self.defaults["betas"], self.defaults["eps"]
+            ens.poll_status()             # the reference exit(-1)s on a loss explosion (render_rays.py:88-90)
             ens.adam_step()
         _DIRTY.clear()
 

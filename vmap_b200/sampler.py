@@ -154,10 +154,18 @@ class SamplerTables:
             self.host = self.host.pin_memory()
         self.dev = torch.zeros(words64, dtype=torch.int64, device=self.device)
         self.image_wh = None            # (W, H) of the per-object keyframe images (per-object mode)
+        self._uploaded = None           # event recorded after the last host->device copy of the pinned buffer
+
+    def _wait_upload(self) -> None:
+        """The pinned buffer may still be the source of an in-flight (asynchronous) upload of the previous frame:
+        wait for that copy -- only the copy, not the frame's kernels -- before overwriting it."""
+        if self._uploaded is not None:
+            self._uploaded.synchronize()
 
     def fill_objects(self, sets: Sequence[KeyframeSet]) -> None:
         B = self.n_obj
         assert self.kf_stride == 0 and len(sets) == B
+        self._wait_upload()
         for o in sets:
             assert o.rgbs_batch.is_contiguous() and o.depth_batch.is_contiguous()
             assert o.t_wc_batch.is_contiguous() and o.bbox.is_contiguous()
@@ -175,6 +183,7 @@ class SamplerTables:
     def fill_store(self, kt: "KeyframeTables") -> None:
         B, KF = self.n_obj, self.kf_stride
         assert kt.kf_slot.shape == (B, KF)
+        self._wait_upload()
         h = self.host.view(torch.int32)
         o = 0
         for t in (kt.kf_slot, kt.kf_bbox.view(torch.int32), kt.obj_id, kt.n_kf, kt.latest):
@@ -183,6 +192,10 @@ class SamplerTables:
 
     def upload(self) -> None:
         self.dev.copy_(self.host, non_blocking=True)
+        if self.dev.is_cuda and not torch.cuda.is_current_stream_capturing():
+            if self._uploaded is None:
+                self._uploaded = torch.cuda.Event()
+            self._uploaded.record(torch.cuda.current_stream(self.device))
 
     def bind(self, a) -> None:
         B, KF = self.n_obj, self.kf_stride

@@ -29,29 +29,24 @@ class Trainer:
 
     def eval_points(self, points, chunk_size=100000):
         """(occupancy [N], colour [N,3]) or None when everything is empty (trainer.py:77-95).
-        ``chunk_size`` is accepted for signature compatibility; the kernel tiles internally."""
+        ``chunk_size`` bounds the points per launch (at least 131072: the kernel tiles internally)."""
         ens = ensemble_for_modules(self.fc_occ_map, self.pe)
         row = self.fc_occ_map._vmb_binding[1]
-        pts = points.to(ens.device, torch.float32).reshape(1, -1, 3)
-        if ens.n_obj > 1:                      # bound into a stack: evaluate through a 1-row view
-            pts = pts.expand(ens.n_obj, -1, -1).contiguous()
-        alpha, colour = ens.eval_points(pts.contiguous())
-        occ = torch.sigmoid(alpha[row])
+        pts = points.to(ens.device, torch.float32).reshape(-1, 3).contiguous()
+        # one-row call: only THIS object's network runs, however many objects share the packed stack
+        alpha, colour = ens.eval_points(pts, row=row, chunk=max(int(chunk_size), 1 << 17))
+        occ = torch.sigmoid(alpha)
         if float(occ.max()) == 0:
             print("no occ")
             return None
-        return occ, colour[row]
+        return occ, colour
 
     def meshing(self, bound, obj_center, grid_dim=256):
-        """Marching-cubes meshing (trainer.py:35-75) needs skimage + trimesh, which are
-        visualisation dependencies outside the accelerated path."""
-        try:
-            import skimage.measure  # noqa: F401
-            import trimesh  # noqa: F401
-        except Exception as e:      # pragma: no cover
-            raise NotImplementedError("meshing needs skimage and trimesh (not part of the hot path)") from e
-        from .meshing import mesh_object
-        return mesh_object(self, bound, obj_center, grid_dim)
+        """Marching-cubes meshing (trainer.py:35-75) is visualisation (skimage + trimesh on the CPU) and out of this
+        path's scope; the part of it that runs the network -- ``eval_points`` on
+        ``make_3D_grid`` points -- is provided above."""
+        raise NotImplementedError("meshing is outside the accelerated path: use eval_points(make_3D_grid(...)) "
+                                  "and run marching cubes with the reference's own trainer.meshing")
 
 
 def make_3D_grid(occ_range=(-1., 1.), dim=256, device="cuda:0", transform=None, scale=None):

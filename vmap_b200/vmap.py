@@ -262,6 +262,13 @@ class sceneObject:
             self.trainer.pe.B_layer.weight.copy_(ck["PE_state_dict"]["B_layer.weight"].to(self.trainer.pe.B_layer.weight.device))
         self.obj_id, self.bbox3d = ck["obj_id"], ck["bbox"]
         self.trainer.obj_scale = ck["obj_scale"]
+        pe = self.trainer.pe
+        if "scale" in ck["PE_state_dict"]:          # persistent buffer of UniDirsEmbed (embedding.py:80): load_state_dict restores it
+            with torch.no_grad():
+                pe.scale.copy_(ck["PE_state_dict"]["scale"].to(pe.scale.device))
         b = getattr(self.trainer.fc_occ_map, "_vmb_binding", None)
         if b is not None and b[0]() is not None:
-            b[0]().refresh_image()
+            ens, row = b[0](), b[1]
+            ens.scale[row] = float(pe.scale)         # the kernels read the packed copy
+            ens.reset_optimizer_row(row)             # freshly loaded weights start AdamW from scratch, like a new param group
+            ens.refresh_image()
