@@ -81,3 +81,44 @@ def test_frame_graph_matches_eager_loop(use_store):
     # later steps: that noise flips the sign of a few L1 residuals (random targets), so trajectories drift a little
     assert torch.allclose(l_e, l_g, rtol=3e-2, atol=1e-3), (l_e, l_g)
     assert rel_l2(p_g, p_e) < 2e-2
+
+
+def test_frame_graph_with_background_model():
+    """do_bg (train.py:147-152,196-206,308-316): the separate background model (hidden 128, 5 + 9 bins) is sampled and
+    stepped inside the same captured frame; graph replay == eager loop, and both models train."""
+    from vmap_b200 import synth
+    from vmap_b200.ensemble import VmapEnsemble
+    from vmap_b200.frame import Background, FrameLoop
+    from vmap_b200.sampler import BatchedSampler
+    B, KF, W, H, n_frames, n_pix, n_iter = 3, 4, 64, 48, 8, 15, 4
+    rays = so.camera_ray_dirs(W, H, 60.0, 60.0, W / 2 - 0.5, H / 2 - 0.5).to(DEV)
+    sets = _objects(B, KF, W, H, seed=1)
+    bg_set = _objects(1, KF, W, H, seed=2)[0]
+    params = synth.init_params(B, 32, seed=0)
+    bg_params = synth.init_params(1, 128, seed=1)
+    results = []
+    for mode in ("eager", "graph"):
+        ens = VmapEnsemble(B, hidden=32, scale=2.0, device=DEV)
+        ens.load_stacked(params)
+        bg_ens = VmapEnsemble(1, hidden=128, scale=10.0, device=DEV)
+        bg_ens.load_stacked(bg_params)
+        p0 = bg_ens.params.clone()
+        bg = Background(bg_ens, BatchedSampler(DEV, 5, 9), n_frames=8, n_pix=10)
+        fl = FrameLoop(ens, BatchedSampler(DEV, 1, 9), n_frames, n_pix, n_iter, rays, seed=5, first_offset=7, background=bg)
+        fl.set_objects(sets)
+        fl.set_background(bg_set)
+        losses = []
+        for frame in range(2):
+            l = fl.run_eager() if mode == "eager" else fl.run()
+            losses.append(l.clone())
+        torch.cuda.synchronize()
+        ens.check_status(); bg_ens.check_status()
+        assert int(bg_ens.step_counter[0]) == 2 * n_iter and bg_ens.step_count == 2 * n_iter
+        assert not torch.equal(bg_ens.params, p0)
+        results.append((torch.stack(losses).cpu(), ens.params.clone(), bg_ens.params.clone(), bg.out["z"].clone()))
+    (l_e, p_e, q_e, z_e), (l_g, p_g, q_g, z_g) = results
+    assert torch.equal(z_e, z_g)                        # the background draws the same 14-sample rays in both modes
+    assert z_e.shape[-1] == 14
+    assert rel_l2(p_g, p_e) < 2e-2
+    assert torch.allclose(l_e, l_g, rtol=3e-2, atol=1e-3), (l_e, l_g)
+    assert rel_l2(q_g, q_e) < 2e-2                      # hidden-128 layer-wise path still reduces wgrads with atomics

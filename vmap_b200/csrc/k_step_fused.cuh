@@ -3,7 +3,7 @@
 //   -> per-object gradient reduction in a fixed order -> AdamW + fp16 weight-image refresh
 // fp16 operands / fp32 accumulate on tcgen05 (TMEM accumulators), weights staged per object with one bulk
 // async copy.  Same decomposition as k_step_umma.cuh (CTA = 2 point groups x 256 threads, a group walks a tile of
-// <= 128 sample points through 12 dependent MMA stages), with what the round-1 cycle trace showed to be on the
+// <= 128 sample points through 12 dependent MMA stages), with what the cycle traces showed to be on the
 // critical path taken off it:
 //   * rays never straddle a warp (32/S rays per warp), so transmittance, the five rendered sums, the variance and
 //     the backward suffix sum are warp-shuffle scans over the sample axis in registers -- no per-ray serial loop,
@@ -36,7 +36,7 @@
 
 struct FusedExtra {
   float* partials;            // [(B + grid)][stride] per-(CTA, object) gradient partials, row = blockIdx + object
-  unsigned int* obj_done;     // [B] segments finished per object (self-resetting)
+  unsigned int* obj_done;     // [B] segments finished per object (non-cooperative), [B] skip flags, [2] grid arrive / depart (self-resetting)
   const int* counts_in;       // optional [B][4] external mask counts (ray-sharded iMAP: all-reduced by the caller)
   int fuse_adam;              // 1: the finisher applies AdamW; 0: it adds the reduced gradient into `grads`
   float* p; float* m; float* v;
@@ -44,9 +44,12 @@ struct FusedExtra {
   int* step_counter;          // optional [B] device step numbers (t = counter + 1, incremented here)
   float step_size, bc2_sqrt;  // host-computed bias corrections when step_counter == nullptr
   double lr, b1d, b2d;
+  float log_b1, log_b2;       // ln(beta1), ln(beta2)
   float lr_wd, one_m_b1, b2, one_m_b2, eps;
   int guard_loss;
   int* status;
+  int single_group;           // 1: only point group 0 walks tiles -> one in-order wgrad MMA stream per SM -> bitwise reproducible
+  int cooperative;            // 1: cooperative launch (all CTAs resident): an object's CTAs share its reduction + update
 };
 
 namespace uf {
@@ -63,9 +66,17 @@ constexpr int MISC_BYTES = 512;
 constexpr int SM_CNT = SM_MISC + MISC_BYTES;                      // int [B][3] mask counts
 constexpr int SMEM_MAX = 232448;
 constexpr int MAX_OBJ_SMEM = (SMEM_MAX - SM_CNT) / 12;            // objects whose counts fit (1062)
-// TMEM columns: persistent wgrad accumulators, then per group {acc[48], spare[16], E[96]}
+// TMEM columns: persistent wgrad accumulators, then per group 160 columns:
+//   backward: acc[0,48) | - | E[64,160) (embedding-gradient tile)
+//   forward : acc[0,32) | hA[32,48) activation A-operand | alpha tile[48,64) | emb1 A-operand[64,112) | emb2 A-operand
+//             [112,136) | colour tile[136,152)             (VMB_TS_FWD: the forward MMAs read A from tensor memory)
+#ifndef VMB_TS_FWD
+#define VMB_TS_FWD 1
+#endif
 constexpr int WG_IN = 0, WG_M1 = 32, WG_CAT = 64, WG_M2 = 96, WG_CL = 128, WG_HD = 160, WG_DB = 176;
 constexpr int ACC0 = 192, ACC_STRIDE = 160, ACC_E = 64;
+constexpr int TC_HA = 32, TC_E1A = 64, TC_E2A = 112;
+constexpr int TC_ALPHA = VMB_TS_FWD ? 48 : 64, TC_COL = VMB_TS_FWD ? 136 : 80;
 constexpr float LS = um::LS, INV_LS = um::INV_LS;
 
 struct Misc {
@@ -149,6 +160,36 @@ struct Issuer {
     constexpr uint32_t KM32 = ptx::idesc_f16(128, 32, 0, 1), KM48 = ptx::idesc_f16(128, 48, 0, 1), KM96 = ptx::idesc_f16(128, 96, 0, 1);
     const uint32_t A = acc, E = acc + ACC_E;
     switch (st) {
+#if VMB_TS_FWD
+      case 0:   // in_layer: emb1 (K = 96), A from tensor memory
+#pragma unroll
+        for (int ks = 0; ks < 6; ++ks) ptx::umma_f16_ts(A, acc + TC_E1A + ks * 8, w_k(um::IMG_WIN, ks), KK32, ks > 0);
+        break;
+      case 1:   // mid1: fc1
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) ptx::umma_f16_ts(A, acc + TC_HA + ks * 8, w_k(um::IMG_WM1, ks), KK32, ks > 0);
+        break;
+      case 2:   // cat_layer: [fc2 | emb1] (K = 128)
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks)
+          ptx::umma_f16_ts(A, ks < 2 ? acc + TC_HA + ks * 8 : acc + TC_E1A + (ks - 2) * 8, w_k(um::IMG_WCAT, ks), KK32, ks > 0);
+        break;
+      case 3:   // mid2: fc3
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) ptx::umma_f16_ts(A, acc + TC_HA + ks * 8, w_k(um::IMG_WM2, ks), KK32, ks > 0);
+        break;
+      case 4:   // color_linear: [fc4 | emb2] (K = 80) -> A ; out_alpha: fc4 -> alpha tile column 0
+#pragma unroll
+        for (int ks = 0; ks < 5; ++ks)
+          ptx::umma_f16_ts(A, ks < 2 ? acc + TC_HA + ks * 8 : acc + TC_E2A + (ks - 2) * 8, w_k(um::IMG_WCL, ks), KK32, ks > 0);
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) ptx::umma_f16_ts(acc + TC_ALPHA, acc + TC_HA + ks * 8, w16_k(um::IMG_WA16, ks), KK16, ks > 0);
+        break;
+      case 5:   // out_color: hc -> its own 16-column tile (columns 1..3), so alpha's tile can be read while this runs
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) ptx::umma_f16_ts(acc + TC_COL, acc + TC_HA + ks * 8, w16_k(um::IMG_WOC16, ks), KK16, ks > 0);
+        break;
+#else
       case 0:   // in_layer: emb1 (K = 96)
 #pragma unroll
         for (int ks = 0; ks < 6; ++ks) ptx::umma_f16(A, a_k(FG_E1, ks), w_k(um::IMG_WIN, ks), KK32, ks > 0);
@@ -165,16 +206,17 @@ struct Issuer {
 #pragma unroll
         for (int ks = 0; ks < 2; ++ks) ptx::umma_f16(A, a_k(FG_FC3, ks), w_k(um::IMG_WM2, ks), KK32, ks > 0);
         break;
-      case 4:   // color_linear: [fc4 | emb2] (K = 80) -> A ; out_alpha: fc4 -> heads tile column 0
+      case 4:   // color_linear: [fc4 | emb2] (K = 80) -> A ; out_alpha: fc4 -> alpha tile column 0
 #pragma unroll
         for (int ks = 0; ks < 5; ++ks) ptx::umma_f16(A, a_k(FG_FC4, ks), w_k(um::IMG_WCL, ks), KK32, ks > 0);
 #pragma unroll
-        for (int ks = 0; ks < 2; ++ks) ptx::umma_f16(E, a_k(FG_FC4, ks), w16_k(um::IMG_WA16, ks), KK16, ks > 0);
+        for (int ks = 0; ks < 2; ++ks) ptx::umma_f16(acc + TC_ALPHA, a_k(FG_FC4, ks), w16_k(um::IMG_WA16, ks), KK16, ks > 0);
         break;
-      case 5:   // out_color: hc -> heads tile columns 1..3 (accumulates onto alpha's tile)
+      case 5:   // out_color: hc -> its own 16-column tile (columns 1..3), so alpha's tile can be read while this runs
 #pragma unroll
-        for (int ks = 0; ks < 2; ++ks) ptx::umma_f16(E, a_k(FG_HC, ks), w16_k(um::IMG_WOC16, ks), KK16, 1u);
+        for (int ks = 0; ks < 2; ++ks) ptx::umma_f16(acc + TC_COL, a_k(FG_HC, ks), w16_k(um::IMG_WOC16, ks), KK16, ks > 0);
         break;
+#endif
       case 6:   // d_hc = dhead @ W_oc
         ptx::umma_f16(A, a_k(FG_DH, 0), w16_mn(um::IMG_WOC16), KM32, 0u);
         break;
@@ -235,14 +277,14 @@ __device__ __forceinline__ int cta_of_tile(long long t, long long T, int G) { re
 // ---------------------------------------------------------------------------------------------------------------
 template <int SC>
 __global__ void __launch_bounds__(uf::NT, 1)
-k_step_fused(StepParams a, FusedExtra x, VmbLayout L, const unsigned char* image, int tpo, int nr, int rpw, long long T) {
+k_step_fused(StepParams a, FusedExtra x, VmbLayout L, const unsigned char* image, int tpo, int npo, int nr, int rpw, long long T) {
   using namespace uf;
   extern __shared__ __align__(1024) unsigned char smem[];
   Misc* misc = reinterpret_cast<Misc*>(smem + SM_MISC);
   int* cnt = reinterpret_cast<int*>(smem + SM_CNT);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int S = SC ? SC : a.S, R = a.R;
-  if (tid == 0) TRF(1, 199);
+  if (tid == 0) TRF(3, 199);
 
   if (tid == 0) {
     ptx::mbar_init(&misc->done[0], 1); ptx::mbar_init(&misc->done[1], 1);
@@ -252,7 +294,13 @@ k_step_fused(StepParams a, FusedExtra x, VmbLayout L, const unsigned char* image
     ptx::mbar_init_fence();
   }
   if (warp == 15) { ptx::tmem_alloc(&misc->tmem_base, 512); ptx::tmem_relinquish(); }
+  const int G = gridDim.x;
+  const long long gt_begin = (T * blockIdx.x) / G, gt_end = (T * (blockIdx.x + 1)) / G;
   __syncthreads();
+  if (tid == 0 && gt_begin < gt_end) {     // first object's weight image: in flight while the mask counts run
+    ptx::mbar_arrive_expect_tx(&misc->wbar, um::IMG_BYTES);
+    ptx::bulk_g2s(smem + SM_W, image + (size_t)(gt_begin / npo) * um::IMG_BYTES, um::IMG_BYTES, &misc->wbar);
+  }
   // ---- K0 in the prologue: mask counts of EVERY object (the any-empty early-out couples them, render_rays.py:68-73)
   if (!a.fwd_only) {
     if (x.counts_in) {
@@ -262,20 +310,14 @@ k_step_fused(StepParams a, FusedExtra x, VmbLayout L, const unsigned char* image
         if (c == 0) misc->on[i % 3] = 0;
       }
     } else {
-      for (int b = warp; b < a.B; b += NT / 32) {
+      // warp w counts objects w, w+16, ...; two objects at a time with every load of both in flight together (the
+      // inputs are cold in HBM: one latency per pair of objects instead of one per 8 words)
+      const int nw = R >> 2;
+      auto finish = [&](int b, int nd, int no, int ns) {
         const unsigned char* s = a.sem + (size_t)b * a.sem_stride;
         const unsigned char* m = a.mask + (size_t)b * a.mask_stride;
-        int nd = 0, no = 0, ns = 0, r_lo = 0;
-        if ((((size_t)s | (size_t)m) & 3) == 0) {                   // four rays per load
-          const int nw = R >> 2;
-          for (int w = lane; w < nw; w += 32) {
-            const uint32_t sv = reinterpret_cast<const uint32_t*>(s)[w], mv = reinterpret_cast<const uint32_t*>(m)[w];
-            const uint32_t so = __vcmpne4(sv, 0u), s2 = __vcmpne4(sv, 0x02020202u), mo = __vcmpne4(mv, 0u);
-            no += __popc(so) >> 3; ns += __popc(s2) >> 3; nd += __popc(so & mo) >> 3;
-          }
-          r_lo = nw << 2;
-        }
-        for (int r = r_lo + lane; r < R; r += 32) {
+        const bool vec = (((size_t)s | (size_t)m) & 3) == 0;
+        for (int r = (vec ? (nw << 2) : 0) + lane; r < R; r += 32) {      // tail rays, or everything when unaligned
           const int sv = s[r], mo = sv != 0;
           nd += (m[r] != 0) & mo; no += mo; ns += sv != 2;
         }
@@ -289,6 +331,38 @@ k_step_fused(StepParams a, FusedExtra x, VmbLayout L, const unsigned char* image
           if (no == 0) misc->on[1] = 0;
           if (ns == 0) misc->on[2] = 0;
         }
+      };
+      for (int bA = warp; bA < a.B; bA += 2 * (NT / 32)) {
+        const int bB = bA + NT / 32;
+        const bool hasB = bB < a.B;
+        const uint32_t* sA = reinterpret_cast<const uint32_t*>(a.sem + (size_t)bA * a.sem_stride);
+        const uint32_t* mA = reinterpret_cast<const uint32_t*>(a.mask + (size_t)bA * a.mask_stride);
+        const uint32_t* sB = reinterpret_cast<const uint32_t*>(a.sem + (size_t)(hasB ? bB : bA) * a.sem_stride);
+        const uint32_t* mB = reinterpret_cast<const uint32_t*>(a.mask + (size_t)(hasB ? bB : bA) * a.mask_stride);
+        const bool vA = (((size_t)sA | (size_t)mA) & 3) == 0, vB = hasB && (((size_t)sB | (size_t)mB) & 3) == 0;
+        int cA[3] = {0, 0, 0}, cB[3] = {0, 0, 0};
+        for (int w0 = 0; w0 < nw; w0 += 320) {                  // four rays per 32-bit load, ten loads per array per lane
+          uint32_t sa[10], ma[10], sb[10], mb[10];
+#pragma unroll
+          for (int u = 0; u < 10; ++u) {
+            const int w = w0 + u * 32 + lane;
+            const bool in = w < nw;
+            sa[u] = (in && vA) ? __ldg(sA + w) : 0u;  ma[u] = (in && vA) ? __ldg(mA + w) : 0u;
+            sb[u] = (in && vB) ? __ldg(sB + w) : 0u;  mb[u] = (in && vB) ? __ldg(mB + w) : 0u;
+          }
+#pragma unroll
+          for (int u = 0; u < 10; ++u) {
+            const int w = w0 + u * 32 + lane;
+            if (w < nw) {
+              uint32_t so = __vcmpne4(sa[u], 0u), s2 = __vcmpne4(sa[u], 0x02020202u), mo = __vcmpne4(ma[u], 0u);
+              if (vA) { cA[1] += __popc(so) >> 3; cA[2] += __popc(s2) >> 3; cA[0] += __popc(so & mo) >> 3; }
+              so = __vcmpne4(sb[u], 0u); s2 = __vcmpne4(sb[u], 0x02020202u); mo = __vcmpne4(mb[u], 0u);
+              if (vB) { cB[1] += __popc(so) >> 3; cB[2] += __popc(s2) >> 3; cB[0] += __popc(so & mo) >> 3; }
+            }
+          }
+        }
+        finish(bA, cA[0], cA[1], cA[2]);
+        if (hasB) finish(bB, cB[0], cB[1], cB[2]);
       }
     }
   }
@@ -304,11 +378,9 @@ k_step_fused(StepParams a, FusedExtra x, VmbLayout L, const unsigned char* image
   }
   ptx::tc_fence_before();
   __syncthreads();
-  if (tid == 0) TRF(1, 200);
+  if (tid == 0) TRF(3, 200);
   ptx::tc_fence_after();
 
-  const int G = gridDim.x;
-  const long long gt_begin = (T * blockIdx.x) / G, gt_end = (T * (blockIdx.x + 1)) / G;
   uint32_t wpar = 0;                  // weight-barrier parity (one completion per segment)
   uint32_t ph = 0, wph = 0;           // parities of this thread's group barriers: stage commits / deferred MMAs
   bool wb_pending = false;            // deferred MMAs of the previous tile not yet known complete
@@ -334,21 +406,135 @@ k_step_fused(StepParams a, FusedExtra x, VmbLayout L, const unsigned char* image
   const bool issuer_warp = (warp & 7) == 0;
   const float on_d = misc->on[0] ? 1.f : 0.f, on_c = misc->on[1] ? 1.f : 0.f, on_o = misc->on[2] ? 1.f : 0.f;
 
-  for (long long gt = gt_begin; gt < gt_end;) {
-    const int b = (int)(gt / tpo);
-    const int t0 = (int)(gt - (long long)b * tpo);
-    const int t1 = (int)min((long long)tpo, (long long)t0 + (gt_end - gt));
-    gt += t1 - t0;
-
-    // ---- stage this object's weight image: one bulk copy global -> shared ------------------------------------
-    if (tid == 0) {
-      ptx::mbar_arrive_expect_tx(&misc->wbar, um::IMG_BYTES);
-      ptx::bulk_g2s(smem + SM_W, image + (size_t)b * um::IMG_BYTES, um::IMG_BYTES, &misc->wbar);
+  // Reduce object b's partial rows over float4 columns [i_lo, i_hi) in segment order (the same sum every run) and either
+  // apply AdamW (fuse_adam) or add the reduced gradient into `grads`.  `owner` writes the object's loss terms / status.
+  // Called by all threads of the CTA; returns the object's skip flag (loss explosion guard, render_rays.py:88-90).
+  auto finish_rows = [&](int b, int i_lo, int i_hi, bool owner) -> int {
+    const int c_first = cta_of_tile((long long)b * npo, T, G), c_last = cta_of_tile((long long)(b + 1) * npo - 1, T, G);
+    const int nseg = c_last - c_first + 1;
+    const int i_sl = owner ? 0 : 1;
+    {
+      const float* P0 = x.partials + (size_t)(c_first + b) * L.stride;
+      if (warp == 0) {
+        // the segments' loss terms: up to ten segments are loaded by 30 lanes at once, then added in segment order
+        float s = 0.f;
+        if (nseg <= 10) {
+          const int k = lane / 3, j = lane - 3 * k;
+          const float v = (k < nseg) ? __ldcg(P0 + (size_t)k * L.stride + L.P + j) : 0.f;
+          for (int kk = 0; kk < nseg; ++kk) s += __shfl_sync(0xffffffffu, v, kk * 3 + (lane < 3 ? lane : 0));
+        } else if (lane < 3) {
+          for (int k = 0; k < nseg; ++k) s += __ldcg(P0 + (size_t)k * L.stride + L.P + lane);
+        }
+        const float l_d = __shfl_sync(0xffffffffu, s, 0), l_c = __shfl_sync(0xffffffffu, s, 1), l_o = __shfl_sync(0xffffffffu, s, 2);
+        if (lane == 0) {
+          const float tot = l_d + a.cs * l_c + a.os * l_o;
+          if (i_sl == 0) { float* lt = a.loss_terms + b * 4; lt[0] = l_d; lt[1] = l_c; lt[2] = l_o; lt[3] = tot; }
+          int bad = 0;                                  // render_rays.py:88-90: the reference aborts before the update
+          if (x.guard_loss) {
+            if (l_d > 100000.f || l_c > 100000.f || l_o > 100000.f) bad |= 1;
+            if (!(tot == tot) || fabsf(tot) > 3.0e38f) bad |= 2;
+            if (bad && x.status && i_sl == 0) atomicOr(x.status, bad);
+          }
+          misc->skip = bad;
+          if (x.fuse_adam && x.step_counter) {
+            // bias corrections 1 - beta^t = -expm1(t log beta): fp32 with the cancellation-free form (<= 3e-7 relative
+            // to torch's double-precision scalars), instead of two double-precision pow calls on the kernel's tail
+            const float t = (float)(x.step_counter[b] + 1);
+            misc->step_size = (float)x.lr / (-expm1f(t * x.log_b1));
+            misc->bc2_sqrt = sqrtf(-expm1f(t * x.log_b2));
+          } else {
+            misc->step_size = x.step_size; misc->bc2_sqrt = x.bc2_sqrt;
+          }
+        }
+      }
+      __syncthreads();
+      if (a.backward && !(misc->skip && x.fuse_adam)) {
+        const float step_size = misc->step_size, bc2_sqrt = misc->bc2_sqrt;
+        const size_t row = (size_t)b * L.stride;
+        const int n4 = L.stride >> 2;
+        for (int i4 = i_lo + tid; i4 < i_hi; i4 += NT) {
+          float4 gsum = make_float4(0.f, 0.f, 0.f, 0.f);
+          const float4* src = reinterpret_cast<const float4*>(P0) + i4;
+          // state loads first, then the partial rows eight at a time (all loads of a batch in flight together);
+          // the additions run in segment order = CTA order: the same sum every run
+          float4 pp = make_float4(0.f, 0.f, 0.f, 0.f), mm = pp, vv = pp;
+          if (x.fuse_adam) {
+            pp = *(reinterpret_cast<const float4*>(x.p + row) + i4);
+            mm = *(reinterpret_cast<const float4*>(x.m + row) + i4);
+            vv = *(reinterpret_cast<const float4*>(x.v + row) + i4);
+          }
+          for (int k0 = 0; k0 < nseg; k0 += 8) {
+            float4 u[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) u[k] = (k0 + k < nseg) ? __ldcg(src + (size_t)(k0 + k) * n4) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+              if (k0 + k < nseg) { gsum.x += u[k].x; gsum.y += u[k].y; gsum.z += u[k].z; gsum.w += u[k].w; }
+          }
+          const int e = i4 * 4;
+          if (!x.fuse_adam) {
+            float4* gd4 = reinterpret_cast<float4*>(a.grads + row) + i4;
+            float4 o = *gd4;
+            o.x += gsum.x; o.y += gsum.y; o.z += gsum.z; o.w += gsum.w;
+            if (e + 3 >= L.P) { if (e + 0 >= L.P) o.x = 0.f; if (e + 1 >= L.P) o.y = 0.f; if (e + 2 >= L.P) o.z = 0.f; o.w = 0.f; }
+            *gd4 = o;
+            continue;
+          }
+          // torch.optim.AdamW._single_tensor_adamw, op for op as k_adamw restates it
+          float* pj = &pp.x; float* mj = &mm.x; float* vj = &vv.x; const float* gj = &gsum.x;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (e + j >= L.P) continue;
+            float pw = pj[j] * x.lr_wd;
+            const float m1 = mj[j] + (gj[j] - mj[j]) * x.one_m_b1;
+            const float v1 = vj[j] * x.b2 + (x.one_m_b2 * gj[j]) * gj[j];
+            const float denom = sqrtf(v1) / bc2_sqrt + x.eps;
+            pw = pw - step_size * (m1 / denom);
+            pj[j] = pw; mj[j] = m1; vj[j] = v1;
+          }
+          *(reinterpret_cast<float4*>(x.p + row) + i4) = pp;
+          *(reinterpret_cast<float4*>(x.m + row) + i4) = mm;
+          *(reinterpret_cast<float4*>(x.v + row) + i4) = vv;
+          if (x.image_out) {
+            __half* img = x.image_out + (size_t)b * x.img_halves;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              if (e + j < L.P) {
+                const int ti = x.img_index[e + j];
+                if (ti >= 0) img[ti] = __float2half_rn(pj[j]);
+                else if (ti <= -2) reinterpret_cast<float*>(img)[-(ti + 2)] = pj[j];
+              }
+            }
+          }
+        }
+      }
     }
+    __syncthreads();
+    const int sk = misc->skip;
+    __syncthreads();                                    // the next call's warp 0 overwrites misc->skip
+    return sk;
+  };
+
+  // The work list is in units of TILE PAIRS (the two point groups of a CTA advance in lock-step rounds, one tile each):
+  // CTA c owns pairs [T c / G, T (c+1) / G), every segment of an object is a whole number of rounds and no CTA runs more
+  // than ceil(T / G) rounds -- with a per-tile split a segment boundary inside a CTA cost it an extra round.
+  for (long long gt = gt_begin; gt < gt_end;) {
+    const int b = (int)(gt / npo);
+    const int p0 = (int)(gt - (long long)b * npo);
+    const int p1 = (int)min((long long)npo, (long long)p0 + (gt_end - gt));
+    gt += p1 - p0;
+    const int t0 = 2 * p0, t1 = min(2 * p1, tpo);       // this segment's tiles of object b
+
+    // ---- this object's weight image (one bulk copy global -> shared, issued before the previous segment's flush) ----
     um::mbar_wait_or_trap(&misc->wbar, wpar);
-    if (tid == 0) TRF(1, 201);
+    if (tid == 0) TRF(3, 201);
     wpar ^= 1;
 
+    float ls_d = 0.f, ls_c = 0.f, ls_o = 0.f;
+    const int t_step = x.single_group ? 1 : 2;
+    const int t_first = x.single_group ? (g == 0 ? t0 : t1) : t0 + g;
+    {
+    // ===================== compute threads of point group g ============================================================
     const float isc = 1.0f / a.scale[b];
     float inv_nd = 0.f, inv_no = 0.f, inv_ns = 0.f;
     if (!a.fwd_only) {
@@ -356,11 +542,20 @@ k_step_fused(StepParams a, FusedExtra x, VmbLayout L, const unsigned char* image
       inv_no = 1.f / ((float)cnt[b * 3 + 1] + 1e-10f);
       inv_ns = 1.f / ((float)cnt[b * 3 + 2] + 1e-10f);
     }
-    float ls_d = 0.f, ls_c = 0.f, ls_o = 0.f;
 
-#define STAGE(ST)                                      \
+    // operands written -> fence for the async proxy -> group barrier -> the elected lane of the group's first warp issues
+    // the stage's MMAs, commits, then issues the layer's weight-gradient MMAs behind the commit -> wait for the accumulator
+    // FWD_HANDOFF: a forward stage's MMAs read their A operand from tensor memory (tcgen05.st by the epilogue, no
+    // generic->async proxy fence on the chain); the shared-memory copies written beside it are first read by
+    // weight-gradient MMAs after stage 6's fence.
+#if VMB_TS_FWD
+#define FWD_HANDOFF() ptx::tmem_st_wait()
+#else
+#define FWD_HANDOFF() ptx::fence_async_smem()
+#endif
+#define STAGE_BEGIN(ST)                                \
   do {                                                 \
-    ptx::fence_async_smem();                           \
+    if ((ST) < 6) FWD_HANDOFF(); else ptx::fence_async_smem(); \
     ptx::tc_fence_before();                            \
     group_bar(g);                                      \
     TRG();                                             \
@@ -373,12 +568,15 @@ k_step_fused(StepParams a, FusedExtra x, VmbLayout L, const unsigned char* image
       }                                                \
       __syncwarp();                                    \
     }                                                  \
-    TRG();                                             \
+  } while (0)
+#define STAGE_END()                                    \
+  do {                                                 \
     um::mbar_wait_or_trap(&misc->done[g], ph);         \
     ph ^= 1;                                           \
     ptx::tc_fence_after();                             \
     TRG();                                             \
   } while (0)
+#define STAGE(ST) do { STAGE_BEGIN(ST); STAGE_END(); } while (0)
     // hidden-layer epilogue on this thread's 16 columns: acc + bias -> ReLU -> fp16 (2 x 16 B)
 #define EPI_RELU(BIAS_OFF, FG)                                                                 \
   do {                                                                                         \
@@ -387,11 +585,15 @@ k_step_fused(StepParams a, FusedExtra x, VmbLayout L, const unsigned char* image
     const float4* bp = reinterpret_cast<const float4*>(wf + (BIAS_OFF) + 16 * hsel);           \
     const float4 b0 = bp[0], b1 = bp[1], b2 = bp[2], b3 = bp[3];                               \
     ptx::tmem_ld_wait();                                                                       \
-    uint4* dst = reinterpret_cast<uint4*>(act + ((FG) + 2 * hsel) * FGB + p * 16);             \
-    dst[0] = make_uint4(pack_relu_h2(v[0] + b0.x, v[1] + b0.y), pack_relu_h2(v[2] + b0.z, v[3] + b0.w),    \
-                        pack_relu_h2(v[4] + b1.x, v[5] + b1.y), pack_relu_h2(v[6] + b1.z, v[7] + b1.w));   \
-    dst[128] = make_uint4(pack_relu_h2(v[8] + b2.x, v[9] + b2.y), pack_relu_h2(v[10] + b2.z, v[11] + b2.w), \
-                          pack_relu_h2(v[12] + b3.x, v[13] + b3.y), pack_relu_h2(v[14] + b3.z, v[15] + b3.w)); \
+    uint32_t hh[8];                                                                            \
+    hh[0] = pack_relu_h2(v[0] + b0.x, v[1] + b0.y);   hh[1] = pack_relu_h2(v[2] + b0.z, v[3] + b0.w);     \
+    hh[2] = pack_relu_h2(v[4] + b1.x, v[5] + b1.y);   hh[3] = pack_relu_h2(v[6] + b1.z, v[7] + b1.w);     \
+    hh[4] = pack_relu_h2(v[8] + b2.x, v[9] + b2.y);   hh[5] = pack_relu_h2(v[10] + b2.z, v[11] + b2.w);   \
+    hh[6] = pack_relu_h2(v[12] + b3.x, v[13] + b3.y); hh[7] = pack_relu_h2(v[14] + b3.z, v[15] + b3.w);   \
+    if (VMB_TS_FWD) ptx::tmem_st8(tA + TC_HA + 8 * hsel, hh);      /* next layer's A operand */              \
+    uint4* dst = reinterpret_cast<uint4*>(act + ((FG) + 2 * hsel) * FGB + p * 16);   /* wgrad's copy */      \
+    dst[0] = make_uint4(hh[0], hh[1], hh[2], hh[3]);                                           \
+    dst[128] = make_uint4(hh[4], hh[5], hh[6], hh[7]);                                         \
   } while (0)
     // dgrad epilogue: dY = (h > 0) * acc; h is read from its own block (FG_H), dY goes to a block whose readers retired
 #define EPI_DGRAD(FG_H, FG_OUT)                                                                \
@@ -428,18 +630,18 @@ k_step_fused(StepParams a, FusedExtra x, VmbLayout L, const unsigned char* image
       }
       n_sm |= 0x10000;                                   // live point
     };
-    prefetch(t0 + g);
+    prefetch(t_first);
 
     int trs = 0;
 #define TRG() do { if (tg == 0) { TRF(g, trs); ++trs; } } while (0)
-    for (int t = t0 + g; t < t1; t += 2) {
+    for (int t = t_first; t < t1; t += t_step) {
       const int ray = t * nr + ray_in_tile;
       TRG();                                            // tile start
       // ---- E0: positional embedding (embedding.py:82-91) ----------------------------------------------------
       const float t0x = nx * isc, t1x = ny * isc, t2x = nz * isc, zv = nzv;
       const float gd = n_gd, gc0 = n_c0, gc1 = n_c1, gc2 = n_c2;
       const int smv = n_sm;
-      prefetch(t + 2);
+      prefetch(t + t_step);
       {
         uint4* e1 = reinterpret_cast<uint4*>(act + FG_E1 * FGB + p * 16);
         uint4* e2 = reinterpret_cast<uint4*>(act + FG_E2 * FGB + p * 16);
@@ -454,17 +656,30 @@ k_step_fused(StepParams a, FusedExtra x, VmbLayout L, const unsigned char* image
           if (q == q0 && wb_pending) {                  // the previous tile's deferred MMAs still read E1 / DPR / FC3
             um::mbar_wait_or_trap(&misc->wb[g], wph); wph ^= 1; wb_pending = false;
           }
-          e1[(2 * q + 1) * 128] = make_uint4(um::pack_h2(sv[0][0], sv[0][1]), um::pack_h2(sv[0][2], sv[0][3]), um::pack_h2(sv[1][0], sv[1][1]), um::pack_h2(sv[1][2], sv[1][3]));
-          e1[(2 * q + 2) * 128] = make_uint4(um::pack_h2(sv[2][0], sv[2][1]), um::pack_h2(sv[2][2], sv[2][3]), um::pack_h2(sv[3][0], sv[3][1]), um::pack_h2(sv[3][2], sv[3][3]));
-          e2[q * 128] = make_uint4(um::pack_h2(sv[0][4], sv[0][5]), um::pack_h2(sv[1][4], sv[1][5]), um::pack_h2(sv[2][4], sv[2][5]), um::pack_h2(sv[3][4], sv[3][5]));
+          const uint4 ua = make_uint4(um::pack_h2(sv[0][0], sv[0][1]), um::pack_h2(sv[0][2], sv[0][3]), um::pack_h2(sv[1][0], sv[1][1]), um::pack_h2(sv[1][2], sv[1][3]));
+          const uint4 ub = make_uint4(um::pack_h2(sv[2][0], sv[2][1]), um::pack_h2(sv[2][2], sv[2][3]), um::pack_h2(sv[3][0], sv[3][1]), um::pack_h2(sv[3][2], sv[3][3]));
+          const uint4 uc = make_uint4(um::pack_h2(sv[0][4], sv[0][5]), um::pack_h2(sv[1][4], sv[1][5]), um::pack_h2(sv[2][4], sv[2][5]), um::pack_h2(sv[3][4], sv[3][5]));
+          e1[(2 * q + 1) * 128] = ua; e1[(2 * q + 2) * 128] = ub; e2[q * 128] = uc;
+          if (VMB_TS_FWD) {       // the same 8-feature chunks as A-operand columns (4 packed columns per chunk)
+            ptx::tmem_st4(tA + TC_E1A + (2 * q + 1) * 4, ua.x, ua.y, ua.z, ua.w);
+            ptx::tmem_st4(tA + TC_E1A + (2 * q + 2) * 4, ub.x, ub.y, ub.z, ub.w);
+            ptx::tmem_st4(tA + TC_E2A + q * 4, uc.x, uc.y, uc.z, uc.w);
+          }
         }
         if (hsel) {
           // direction 20 shares chunk 0 of emb1 with [1, x, y, z] and chunk 5 of emb2 with the const-1 column
           float s[6];
           um::sin_ladder(fmaf(Bd[62], t2x, fmaf(Bd[61], t1x, Bd[60] * t0x)), s);
-          e1[0] = make_uint4(um::pack_h2(1.0f, t0x), um::pack_h2(t1x, t2x), um::pack_h2(s[0], s[1]), um::pack_h2(s[2], s[3]));
-          e2[5 * 128] = make_uint4(um::pack_h2(s[4], s[5]), um::pack_h2(1.0f, 0.f), 0u, 0u);
+          const uint4 u0 = make_uint4(um::pack_h2(1.0f, t0x), um::pack_h2(t1x, t2x), um::pack_h2(s[0], s[1]), um::pack_h2(s[2], s[3]));
+          const uint4 u5 = make_uint4(um::pack_h2(s[4], s[5]), um::pack_h2(1.0f, 0.f), 0u, 0u);
+          e1[0] = u0;
+          e2[5 * 128] = u5;
           e1[11 * 128] = make_uint4(0u, 0u, 0u, 0u);
+          if (VMB_TS_FWD) {
+            ptx::tmem_st4(tA + TC_E1A, u0.x, u0.y, u0.z, u0.w);
+            ptx::tmem_st4(tA + TC_E2A + 20, u5.x, u5.y, u5.z, u5.w);
+            ptx::tmem_st4(tA + TC_E1A + 44, 0u, 0u, 0u, 0u);
+          }
           // zero this point's dhead row (cols 4..15 stay zero; 0..3 are written after the render)
           uint4* dh = reinterpret_cast<uint4*>(act + FG_DH * FGB + p * 16);
           dh[0] = make_uint4(0u, 0u, 0u, 0u); dh[128] = make_uint4(0u, 0u, 0u, 0u);
@@ -486,15 +701,46 @@ k_step_fused(StepParams a, FusedExtra x, VmbLayout L, const unsigned char* image
       STAGE(4);                                         // color_linear + out_alpha
       EPI_RELU(um::F_BCL, FG_HC);
       TRG();
-      STAGE(5);                                         // out_color
+      STAGE_BEGIN(5);                                   // out_color runs while the alpha-only part of the render is computed
       // ---- heads + volume render + losses + ray gradients, all in registers of the hsel == 0 warps ---------------
+      // rays never straddle a warp: the scans over the sample axis are warp shuffles
       const bool live = (smv & 0x10000) != 0;
+      auto raysum = [&](float v) {                      // per-ray sum: guarded tree reduction to the ray's first lane, broadcast
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+          if (off < S) { const float u = __shfl_down_sync(0xffffffffu, v, off); if (sidx + off < S) v += u; }
+        }
+        return __shfl_sync(0xffffffffu, v, seg_lo);
+      };
+      float araw = 0.f, occ = 0.f, fr = 1.f, Tr = 1.f, w = 0.f, D = 0.f, O = 0.f, V = 0.f;
+      if (hsel == 0) {                                  // alpha's tile was complete with stage 4
+        float hv[8];
+        um::tmem_ld8(tA + TC_ALPHA, hv);
+        ptx::tmem_ld_wait();
+        araw = (hv[0] + wf[um::F_BA]) * 10.0f;                                   // model.py:77
+        occ = um::fast_sigmoid(araw);                                            // render_rays.py:6
+        if (!a.fwd_only) {
+          if (!live) occ = 0.f;
+          // termination: T_s = prod_{j<s} (1 - occ_j + 1e-10) (render_rays.py:29), inclusive scan then shift
+          fr = 1.f - occ + 1e-10f;
+          float inc = fr;
+#pragma unroll
+          for (int off = 1; off < 32; off <<= 1) {
+            if (off < S) { const float u = __shfl_up_sync(0xffffffffu, inc, off); if (sidx >= off) inc *= u; }
+          }
+          Tr = __shfl_up_sync(0xffffffffu, inc, 1);
+          if (sidx == 0) Tr = 1.f;
+          w = occ * Tr;                                                           // render_rays.py:34
+          D = raysum(w * zv); O = raysum(w);
+          const float dz = zv - D;
+          V = raysum(w * dz * dz);                                                // render_rays.py:47-51 (detached)
+        }
+      }
+      STAGE_END();
       if (hsel == 0) {
         float hv[8];
-        um::tmem_ld8(tE, hv);
+        um::tmem_ld8(tA + TC_COL, hv);
         ptx::tmem_ld_wait();
-        const float araw = (hv[0] + wf[um::F_BA]) * 10.0f;                       // model.py:77
-        float occ = um::fast_sigmoid(araw);                                      // render_rays.py:6
         const float c0 = um::fast_sigmoid(hv[1] + wf[um::F_BOC + 0]), c1 = um::fast_sigmoid(hv[2] + wf[um::F_BOC + 1]),
                     c2 = um::fast_sigmoid(hv[3] + wf[um::F_BOC + 2]);
         if (a.fwd_only) {                               // eval_points (trainer.py:77-90): raw alpha*10, sigmoid colour per point
@@ -505,28 +751,7 @@ k_step_fused(StepParams a, FusedExtra x, VmbLayout L, const unsigned char* image
             oc[0] = c0; oc[1] = c1; oc[2] = c2;
           }
         } else {
-          if (!live) occ = 0.f;
-          // termination: T_s = prod_{j<s} (1 - occ_j + 1e-10) (render_rays.py:29), inclusive scan then shift
-          const float fr = 1.f - occ + 1e-10f;
-          float inc = fr;
-#pragma unroll
-          for (int off = 1; off < 32; off <<= 1) {
-            if (off < S) { const float u = __shfl_up_sync(0xffffffffu, inc, off); if (sidx >= off) inc *= u; }
-          }
-          float Tr = __shfl_up_sync(0xffffffffu, inc, 1);
-          if (sidx == 0) Tr = 1.f;
-          const float w = occ * Tr;                                               // render_rays.py:34
-          // per-ray sums over the sample axis: guarded tree reduction to the ray's first lane, then broadcast
-          auto raysum = [&](float v) {
-#pragma unroll
-            for (int off = 1; off < 32; off <<= 1) {
-              if (off < S) { const float u = __shfl_down_sync(0xffffffffu, v, off); if (sidx + off < S) v += u; }
-            }
-            return __shfl_sync(0xffffffffu, v, seg_lo);
-          };
-          const float D = raysum(w * zv), O = raysum(w), C0 = raysum(w * c0), C1 = raysum(w * c1), C2 = raysum(w * c2);
-          const float dz = zv - D;
-          const float V = raysum(w * dz * dz);                                    // render_rays.py:47-51 (detached)
+          const float C0 = raysum(w * c0), C1 = raysum(w * c1), C2 = raysum(w * c2);
           const int sv = smv & 0xff, mv = (smv >> 8) & 0xff;
           const float m_o = (live && sv != 0) ? 1.f : 0.f, m_s = (live && sv != 2) ? 1.f : 0.f, m_d = (mv != 0) ? m_o : 0.f;
           const float info = 1.f / (sqrtf(V) + 1e-4f);                            // render_rays.py:74-79
@@ -640,8 +865,13 @@ k_step_fused(StepParams a, FusedExtra x, VmbLayout L, const unsigned char* image
 #undef EPI_RELU
 #undef EPI_DGRAD
     if (wb_pending) { um::mbar_wait_or_trap(&misc->wb[g], wph); wph ^= 1; wb_pending = false; }
+    }   // compute threads
     if (a.fwd_only) {                                   // nothing to reduce; the weight buffer is free once both groups are done
       __syncthreads();
+      if (tid == 0 && gt < gt_end) {
+        ptx::mbar_arrive_expect_tx(&misc->wbar, um::IMG_BYTES);
+        ptx::bulk_g2s(smem + SM_W, image + (size_t)(gt / npo) * um::IMG_BYTES, um::IMG_BYTES, &misc->wbar);
+      }
       continue;
     }
     // ---- segment end: this CTA's partial sums for object b -----------------------------------------------------
@@ -649,8 +879,12 @@ k_step_fused(StepParams a, FusedExtra x, VmbLayout L, const unsigned char* image
     if (hsel == 0 && lane == 0) { float* l = misc->lsum[g * 4 + quad]; l[0] = ls_d; l[1] = ls_c; l[2] = ls_o; }
     ptx::tc_fence_before();
     __syncthreads();
-    if (tid == 0) TRF(1, 202);
+    if (tid == 0) TRF(3, 202);
     ptx::tc_fence_after();
+    if (tid == 0 && gt < gt_end) {          // every MMA of this segment has completed: the weight buffer is free --
+      ptx::mbar_arrive_expect_tx(&misc->wbar, um::IMG_BYTES);        // the next object's image lands during the flush
+      ptx::bulk_g2s(smem + SM_W, image + (size_t)(gt / npo) * um::IMG_BYTES, um::IMG_BYTES, &misc->wbar);
+    }
     float* Pr = x.partials + (size_t)(blockIdx.x + b) * L.stride;
     if (tid < 3) {                                      // fixed summation order -> reproducible loss terms
       float s = 0.f;
@@ -696,109 +930,68 @@ k_step_fused(StepParams a, FusedExtra x, VmbLayout L, const unsigned char* image
       }
       ptx::tmem_st_wait();
     }
-    // ---- last segment of the object to arrive reduces the partial rows and applies the update -------------------
-    __threadfence();
-    ptx::tc_fence_before();
-    __syncthreads();
-    ptx::tc_fence_after();
-    const int c_first = cta_of_tile((long long)b * tpo, T, G), c_last = cta_of_tile((long long)(b + 1) * tpo - 1, T, G);
-    const int nseg = c_last - c_first + 1;
-    if (tid == 0) {
-      const unsigned int old = atomicAdd(&x.obj_done[b], 1u);
-      misc->fin = (old + 1u == (unsigned int)nseg) ? 1 : 0;
-    }
-    __syncthreads();
-    if (misc->fin) {
+    // ---- reduce + update ---------------------------------------------------------------------------------------------
+    // cooperative launch: after the LAST segment (below, outside this loop), all CTAs share the reduction of all objects.
+    // otherwise: the last segment of the object to arrive reduces that object's rows here.
+    if (!x.cooperative) {
       __threadfence();
-      const float* P0 = x.partials + (size_t)(c_first + b) * L.stride;
-      if (warp == 0) {
-        float s = 0.f;
-        if (lane < 3) for (int k = 0; k < nseg; ++k) s += __ldcg(P0 + (size_t)k * L.stride + L.P + lane);
-        const float l_d = __shfl_sync(0xffffffffu, s, 0), l_c = __shfl_sync(0xffffffffu, s, 1), l_o = __shfl_sync(0xffffffffu, s, 2);
-        if (lane == 0) {
-          const float tot = l_d + a.cs * l_c + a.os * l_o;
-          float* lt = a.loss_terms + b * 4;
-          lt[0] = l_d; lt[1] = l_c; lt[2] = l_o; lt[3] = tot;
-          int bad = 0;                                  // render_rays.py:88-90: the reference aborts before the update
-          if (x.guard_loss) {
-            if (l_d > 100000.f || l_c > 100000.f || l_o > 100000.f) bad |= 1;
-            if (!(tot == tot) || fabsf(tot) > 3.0e38f) bad |= 2;
-            if (bad && x.status) atomicOr(x.status, bad);
-          }
-          misc->skip = bad;
-          if (x.fuse_adam && x.step_counter) {
-            const double t = (double)(x.step_counter[b] + 1);
-            misc->step_size = (float)(x.lr / (1.0 - pow(x.b1d, t)));
-            misc->bc2_sqrt = (float)sqrt(1.0 - pow(x.b2d, t));
-          } else {
-            misc->step_size = x.step_size; misc->bc2_sqrt = x.bc2_sqrt;
-          }
-        }
-      }
       __syncthreads();
-      if (a.backward && !(misc->skip && x.fuse_adam)) {
-        const float step_size = misc->step_size, bc2_sqrt = misc->bc2_sqrt;
-        const size_t row = (size_t)b * L.stride;
-        const int n4 = L.stride >> 2;
-        for (int i4 = tid; i4 < n4; i4 += NT) {
-          float4 gsum = make_float4(0.f, 0.f, 0.f, 0.f);
-          const float4* src = reinterpret_cast<const float4*>(P0) + i4;
-          for (int k = 0; k < nseg; ++k) {              // segment order = CTA order: the same sum every run
-            const float4 u = __ldcg(src + (size_t)k * n4);
-            gsum.x += u.x; gsum.y += u.y; gsum.z += u.z; gsum.w += u.w;
-          }
-          const int e = i4 * 4;
-          if (!x.fuse_adam) {
-            float4* gd4 = reinterpret_cast<float4*>(a.grads + row) + i4;
-            float4 o = *gd4;
-            o.x += gsum.x; o.y += gsum.y; o.z += gsum.z; o.w += gsum.w;
-            if (e + 3 >= L.P) { if (e + 0 >= L.P) o.x = 0.f; if (e + 1 >= L.P) o.y = 0.f; if (e + 2 >= L.P) o.z = 0.f; o.w = 0.f; }
-            *gd4 = o;
-            continue;
-          }
-          // torch.optim.AdamW._single_tensor_adamw, op for op as k_adamw restates it
-          float4 pp = *(reinterpret_cast<const float4*>(x.p + row) + i4);
-          float4 mm = *(reinterpret_cast<const float4*>(x.m + row) + i4);
-          float4 vv = *(reinterpret_cast<const float4*>(x.v + row) + i4);
-          float* pj = &pp.x; float* mj = &mm.x; float* vj = &vv.x; const float* gj = &gsum.x;
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            if (e + j >= L.P) continue;
-            float pw = pj[j] * x.lr_wd;
-            const float m1 = mj[j] + (gj[j] - mj[j]) * x.one_m_b1;
-            const float v1 = vj[j] * x.b2 + (x.one_m_b2 * gj[j]) * gj[j];
-            const float denom = sqrtf(v1) / bc2_sqrt + x.eps;
-            pw = pw - step_size * (m1 / denom);
-            pj[j] = pw; mj[j] = m1; vj[j] = v1;
-          }
-          *(reinterpret_cast<float4*>(x.p + row) + i4) = pp;
-          *(reinterpret_cast<float4*>(x.m + row) + i4) = mm;
-          *(reinterpret_cast<float4*>(x.v + row) + i4) = vv;
-          if (x.image_out) {
-            __half* img = x.image_out + (size_t)b * x.img_halves;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              if (e + j < L.P) {
-                const int ti = x.img_index[e + j];
-                if (ti >= 0) img[ti] = __float2half_rn(pj[j]);
-                else if (ti <= -2) reinterpret_cast<float*>(img)[-(ti + 2)] = pj[j];
-              }
-            }
-          }
+      const int c_first = cta_of_tile((long long)b * npo, T, G), c_last = cta_of_tile((long long)(b + 1) * npo - 1, T, G);
+      if (tid == 0) misc->fin = (atomicAdd(&x.obj_done[b], 1u) + 1u == (unsigned int)(c_last - c_first + 1)) ? 1 : 0;
+      __syncthreads();
+      if (misc->fin) {
+        __threadfence();
+        const int skip = finish_rows(b, 0, L.stride >> 2, true);
+        if (tid == 0) {
+          x.obj_done[b] = 0u;
+          if (x.fuse_adam && x.step_counter && a.backward && !skip) x.step_counter[b] += 1;
         }
-      }
-      if (tid == 0) {
-        x.obj_done[b] = 0u;
-        if (x.fuse_adam && x.step_counter && a.backward && !misc->skip) x.step_counter[b] += 1;
       }
     }
     ptx::tc_fence_before();
     __syncthreads();
-    if (tid == 0) TRF(1, 203);
+    if (tid == 0) TRF(3, 203);
     ptx::tc_fence_after();
   }
 
-  if (tid == 0) TRF(1, 204);
+  if (x.cooperative && !a.fwd_only) {
+    // ---- grid-wide finish: every CTA is resident (cooperative launch), all of them end their tiles within one round
+    // of each other, and the reduction of ALL objects' partial rows + AdamW is split evenly over the grid (less than one
+    // float4 of the parameter block per thread) instead of one object per SM on the kernel's tail.
+    unsigned int* gbar = x.obj_done + 2 * a.B;          // [0] arrive, [1] depart;  x.obj_done[B + b] = skip flag of object b
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+      atomicAdd(&gbar[0], 1u);
+      unsigned int spins = 0;
+      while (atomicAdd(&gbar[0], 0u) < (unsigned int)G) { __nanosleep(32); if (++spins > 400000000u) __trap(); }
+    }
+    __syncthreads();
+    __threadfence();
+    if (tid == 0) TRF(3, 205);
+    const int n4 = L.stride >> 2;
+    const long long W = (long long)a.B * n4;
+    const long long lo = (W * blockIdx.x) / G, hi = (W * (blockIdx.x + 1)) / G;
+    for (int b = (int)(lo / n4); (long long)b * n4 < hi; ++b) {
+      const int i_lo = (int)(max(lo, (long long)b * n4) - (long long)b * n4);
+      const int i_hi = (int)(min(hi, (long long)(b + 1) * n4) - (long long)b * n4);
+      const int skip = finish_rows(b, i_lo, i_hi, i_lo == 0);
+      if (i_lo == 0 && tid == 0) x.obj_done[a.B + b] = (unsigned int)skip;
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) misc->fin = (atomicAdd(&gbar[1], 1u) + 1u == (unsigned int)G) ? 1 : 0;
+    __syncthreads();
+    if (misc->fin) {                                    // the last CTA to leave: step numbers, re-arm the barrier
+      __threadfence();
+      if (x.fuse_adam && x.step_counter && a.backward)
+        for (int b = tid; b < a.B; b += NT) if (x.obj_done[a.B + b] == 0u) x.step_counter[b] += 1;
+      __syncthreads();
+      if (tid == 0) { gbar[0] = 0u; gbar[1] = 0u; }
+    }
+  }
+
+  if (tid == 0) TRF(3, 204);
   if (warp == 15) ptx::tmem_dealloc(tm, 512);
 }
 
@@ -826,16 +1019,35 @@ static int fused_launch_step(const VmbLayout& L, const StepParams& sp, const Fus
   }
   const int rpw = 32 / sp.S;                  // whole rays per warp: the sample axis never crosses a warp
   const int nr = 4 * rpw;
-  const int tpo = (sp.R + nr - 1) / nr;
-  const long long T = (long long)tpo * sp.B;
-  long long grid = (T + 1) / 2;
+  const int tpo = (sp.R + nr - 1) / nr;       // tiles per object
+  const int npo = (tpo + 1) / 2;              // rounds (tile pairs) per object
+  const long long T = (long long)npo * sp.B;
+  long long grid = T;
   if (grid > n_sm) grid = n_sm;
   if (grid < 1) grid = 1;
   const unsigned char* img = (const unsigned char*)image;
-  if (sp.S == 10)      k_step_fused<10><<<(unsigned)grid, NT, smem_bytes, st>>>(sp, fx, L, img, tpo, nr, rpw, T);
-  else if (sp.S == 14) k_step_fused<14><<<(unsigned)grid, NT, smem_bytes, st>>>(sp, fx, L, img, tpo, nr, rpw, T);
-  else                 k_step_fused<0><<<(unsigned)grid, NT, smem_bytes, st>>>(sp, fx, L, img, tpo, nr, rpw, T);
-  cudaError_t e = cudaGetLastError();
+  FusedExtra fxl = fx;
+  // every CTA is resident (grid <= #SMs, one CTA per SM) -- the cooperative attribute makes the runtime guarantee it,
+  // which is what lets an object's CTAs wait for each other in the shared reduction
+  static int coop_ok[64] = {};
+  if (coop_ok[dev & 63] == 0) {
+    int v = 0;
+    cudaDeviceGetAttribute(&v, cudaDevAttrCooperativeLaunch, dev);
+    coop_ok[dev & 63] = v ? 1 : -1;
+  }
+  fxl.cooperative = (coop_ok[dev & 63] == 1 && !sp.fwd_only && getenv("VMB_NO_COOP") == nullptr) ? 1 : 0;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(NT); cfg.dynamicSmemBytes = smem_bytes; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeCooperative;
+  attr[0].val.cooperative = fxl.cooperative;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  cudaError_t e;
+  if (sp.S == 10)      e = cudaLaunchKernelEx(&cfg, k_step_fused<10>, sp, fxl, L, img, tpo, npo, nr, rpw, T);
+  else if (sp.S == 14) e = cudaLaunchKernelEx(&cfg, k_step_fused<14>, sp, fxl, L, img, tpo, npo, nr, rpw, T);
+  else                 e = cudaLaunchKernelEx(&cfg, k_step_fused<0>, sp, fxl, L, img, tpo, npo, nr, rpw, T);
+  if (e == cudaSuccess) e = cudaGetLastError();
   if (e != cudaSuccess) { err = std::string("k_step_fused launch: ") + cudaGetErrorString(e); return -2; }
   return 0;
 }

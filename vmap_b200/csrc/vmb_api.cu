@@ -197,8 +197,8 @@ static int fused_scratch(vmb_handle* h, cudaStream_t st) {
     return fail(h, VMB_E_CUDA, "vmb_step: first fused step of a handle must run outside stream capture (scratch allocation)");
   const size_t rows = (size_t)fused_rows_needed(h->max_obj, h->n_sm);
   cudaError_t e = cudaMalloc(&h->d_partials, rows * h->L.stride * sizeof(float));
-  if (e == cudaSuccess) e = cudaMalloc(&h->d_objdone, sizeof(unsigned int) * (size_t)h->max_obj);
-  if (e == cudaSuccess) e = cudaMemset(h->d_objdone, 0, sizeof(unsigned int) * (size_t)h->max_obj);
+  if (e == cudaSuccess) e = cudaMalloc(&h->d_objdone, sizeof(unsigned int) * (2 * (size_t)h->max_obj + 8));
+  if (e == cudaSuccess) e = cudaMemset(h->d_objdone, 0, sizeof(unsigned int) * (2 * (size_t)h->max_obj + 8));
   if (e != cudaSuccess) return fail(h, VMB_E_NOMEM, cudaGetErrorString(e));
   return VMB_OK;
 }
@@ -207,6 +207,14 @@ static bool use_v6_kernel() {      // VMB_K1=v6: the round-1 kernel chain (K0 + 
   static int v = -1;
   if (v < 0) { const char* e = getenv("VMB_K1"); v = (e && !strcmp(e, "v6")) ? 1 : 0; }
   return v == 1;
+}
+
+// VMB_DETERMINISTIC=1: one point group per CTA walks the tiles, so every wgrad accumulator receives ONE in-order stream
+// of MMAs and the step is bitwise reproducible (default: two groups interleave their MMAs in arrival order -- still no
+// floating-point atomics, but the fp32 summation order of the two tile streams inside an SM varies from run to run)
+static bool deterministic_mode() {
+  const char* e = getenv("VMB_DETERMINISTIC");
+  return e && e[0] == '1';
 }
 
 static int launch_adamw(vmb_handle* h, int n_obj, float* params, float* grads, float* m, float* v, void* image,
@@ -221,6 +229,7 @@ static int launch_adamw(vmb_handle* h, int n_obj, float* params, float* grads, f
   p.loss_terms = loss_terms; p.status = status;
   p.lr_wd = q.lr_wd; p.one_m_b1 = q.one_m_b1; p.b2 = q.b2; p.one_m_b2 = q.one_m_b2;
   p.step_counter = step_counter; p.ticket = h->d_ticket; p.lr = q.lr; p.b1 = q.b1; p.b2d = q.b2d;
+  p.log_b1 = (float)std::log(q.b1); p.log_b2 = (float)std::log(q.b2d);
   p.step_size = q.step_size; p.bc2_sqrt = q.bc2_sqrt;
   p.eps = eps;
   p.zero_grads = zero_grads;
@@ -274,11 +283,13 @@ int vmb_step(vmb_handle* h, const vmb_step_args* a, void* stream) {
     memset(&fx, 0, sizeof(fx));
     fx.partials = h->d_partials; fx.obj_done = h->d_objdone; fx.counts_in = a->counts;
     fx.fuse_adam = a->fuse_adam ? 1 : 0;
+    fx.single_group = deterministic_mode() ? 1 : 0;
     if (a->fuse_adam) {
       fx.p = const_cast<float*>(a->params); fx.m = a->exp_avg; fx.v = a->exp_avg_sq;
       fx.image_out = (__half*)const_cast<void*>(a->image); fx.img_index = h->d_img_index; fx.img_halves = h->img_halves;
       fx.step_counter = a->step_counter; fx.step_size = q.step_size; fx.bc2_sqrt = q.bc2_sqrt;
       fx.lr = q.lr; fx.b1d = q.b1; fx.b2d = q.b2d;
+      fx.log_b1 = (float)std::log(q.b1); fx.log_b2 = (float)std::log(q.b2d);
       fx.lr_wd = q.lr_wd; fx.one_m_b1 = q.one_m_b1; fx.b2 = q.b2; fx.one_m_b2 = q.one_m_b2; fx.eps = a->eps;
       fx.guard_loss = a->guard_loss; fx.status = a->status;
     }
