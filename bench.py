@@ -376,7 +376,7 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     impl = os.environ.get("VMB_IMPL", "auto")
-    fused = os.environ.get("VMB_K1", "") != "v6" and impl in ("auto", "umma")
+    fused = impl in ("auto", "umma")
 
     sampler = ClockSampler(local)                 # runs for the whole process; windowed to the timed arms below
     if rank == 0:
@@ -532,7 +532,7 @@ def run_ours(args):
                          "traffic": k1_dram_traffic() if fused and world == 1 else None,
                          "traffic_source": "profiles/r02_k_step_fused_ncu_summary.txt (ncu --set full of this command)",
                          "peak_source": src + " bf16 burst",
-                         "peak_sustained": bf16_sust, "kernel": "k_step_fused" if fused else ("k_step_umma" if impl in ("auto", "umma") else "k_step_fp32"),
+                         "peak_sustained": bf16_sust, "kernel": "k_step_fused" if fused else ("k_step_fp32" if impl == "fp32" else "layer-wise"),
                          "kernel_does": "mask counts + PE + MLP + render + loss + backward + ordered gradient reduction + AdamW" if fused else "K1 only",
                          "kernel_us": k1_avg_ms * 1e3, "kernel_us_median": k1_ms[len(k1_ms) // 2] * 1e3,
                          "flop_per_launch": flop_k1,

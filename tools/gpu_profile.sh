@@ -3,8 +3,8 @@
 mkdir -p gpurun_out
 case "$1" in
   k1)        # one full capture of the fused step kernel (forward+backward), BASELINE cfg 2
-    VMB_GRAPHS=0 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_step_umma -s 4 -c 1 \
-      -o gpurun_out/prof_k_step_umma -f python bench.py --steps 4 --warmup 3 --no-cpu > gpurun_out/ncu_full.log 2>&1 ;;
+    VMB_GRAPHS=0 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_step_fused -s 4 -c 1 \
+      -o gpurun_out/prof_k_step_fused -f python bench.py --steps 4 --warmup 3 --no-cpu > gpurun_out/ncu_full.log 2>&1 ;;
   launches)  # launch list of a short bench run (per-kernel durations; cold cache, serialised)
     timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -s 20 -c 60 --csv \
       --log-file gpurun_out/launches.csv python bench.py --steps 12 --warmup 3 --no-cpu > gpurun_out/ncu_bench.log 2>&1 ;;

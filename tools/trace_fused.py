@@ -47,3 +47,12 @@ for g in range(2):
 t = buf[3]
 print("coarse (cycles from kernel entry): setup+counts done %d, weights landed %d, tiles done %d, flush done %d, grid barrier passed %d, end %d" %
       tuple(int(t[i] - t[199]) for i in (200, 201, 202, 203, 205, 204)))
+if os.environ.get("TRACE_E0"):
+    t2 = buf[2]
+    print("--- PE-forward phase of group 0, thread 0 (hsel = 0: three 4-direction iterations): cycles")
+    for tile in range(4):
+        seg = t2[16 * tile:16 * tile + 8]
+        if seg[0] == 0:
+            break
+        d = np.diff(seg[seg != 0])
+        print(f"tile {tile}: prefetch issue, [ladder, stores(+wait on the previous tile's deferred MMAs at iteration 0)] x3:", d.tolist())

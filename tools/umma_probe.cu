@@ -1,5 +1,5 @@
 // Bring-up probe: checks the no-swizzle UMMA shared-memory descriptor conventions used by
-// k_step_umma.cuh (K-major and MN-major operands, LBO/SBO roles) and the TMEM load mapping
+// k_step_fused.cuh (K-major and MN-major operands, LBO/SBO roles) and the TMEM load mapping
 // against a CPU GEMM.  Usage: umma_probe <a_mn_major> <b_mn_major> <swap_lbo_sbo>
 #include <cstdio>
 #include <cstdlib>

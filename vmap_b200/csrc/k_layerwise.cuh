@@ -4,7 +4,7 @@
 // (k_gemm_umma.cuh) over ALL points of the object, activations living in an L2-resident workspace;
 // the thin stages between the GEMMs (positional embedding, heads, volume render + loss, head
 // gradients, PE gradient) are small CUDA-core kernels.  Same arithmetic and the same reference lines
-// as k_step_fp32.cuh / k_step_umma.cuh: embedding.py:82-91, model.py:54-85, render_rays.py:4-96,
+// as k_step_fp32.cuh / k_step_fused.cuh: embedding.py:82-91, model.py:54-85, render_rays.py:4-96,
 // loss.py:5-62 and their backward.
 //
 // Workspace row layouts (fp16 unless noted), P = R*S points of the object:

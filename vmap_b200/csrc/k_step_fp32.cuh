@@ -1,7 +1,7 @@
 // K1 (fp32 flavour): fused PE -> MLP -> volume render -> loss -> backward for a stack of
 // per-object MLPs, CUDA-core fp32 throughout.  Any hidden size; this is the parity anchor
 // (<= ~1e-5 rel-L2 vs the reference's fp32 functorch path) and the path used for the
-// H=128 background model and the H=256 iMAP model.  The H=32 fast path is k_step_umma.cuh.
+// H=128 background model and the H=256 iMAP model.  The H=32 fast path is k_step_fused.cuh.
 //
 // Reference arithmetic restated here:
 //   embedding.py:82-91  (UniDirsEmbed.forward)      model.py:54-85   (OccupancyMap.forward)

@@ -2,9 +2,19 @@
 //   mask counts (render_rays.py:68,86) -> PE -> MLP -> volume render -> losses -> backward
 //   -> per-object gradient reduction in a fixed order -> AdamW + fp16 weight-image refresh
 // fp16 operands / fp32 accumulate on tcgen05 (TMEM accumulators), weights staged per object with one bulk
-// async copy.  Same decomposition as k_step_umma.cuh (CTA = 2 point groups x 256 threads, a group walks a tile of
-// <= 128 sample points through 12 dependent MMA stages), with what the cycle traces showed to be on the
-// critical path taken off it:
+// async copy.  CTA = 2 point groups x 256 threads; a group owns a tile of up to 128 sample points (whole rays; one TMEM
+// lane = one point, two threads per point split the accumulator columns / PE directions) and walks it through 12
+// dependent MMA stages (6 forward, 6 backward): threads write the stage's operands -> group barrier -> one elected
+// lane of the group's first warp issues the tcgen05.mma batch and commits to the group's mbarrier -> threads read the
+// accumulator back with tcgen05.ld.  The two groups are independent, so one group's epilogue overlaps the other's
+// MMAs.  Shared-memory operand layout: SWIZZLE_NONE 8x8 core matrices, an activation block is
+// [feature-group (8 feats)][point][8 feats] halves -- the same bytes serve as a K-major A operand (dgrad: M = points,
+// K = features) and as an MN-major operand (wgrad: M or N = features, K = points).  Weight gradients accumulate in
+// TMEM across all the tiles a CTA owns for an object.  What the round-1 / round-2 cycle traces showed to be on the
+// critical path is off it:
+//   * the forward MMAs read their A operand from TENSOR MEMORY (tcgen05.mma [d], [a_tmem], b_desc: 16 cycles at N = 32
+//     instead of 40, tools/umma_bench2.cu): PE and the layer epilogues tcgen05.st the fp16 rows beside the shared-memory
+//     copy the weight-gradient MMAs need later, and no generic->async proxy fence sits on the forward chain;
 //   * rays never straddle a warp (32/S rays per warp), so transmittance, the five rendered sums, the variance and
 //     the backward suffix sum are warp-shuffle scans over the sample axis in registers -- no per-ray serial loop,
 //     no fp32 scratch rows in shared memory;
@@ -22,16 +32,23 @@
 // backward (train.py:293-324) and torch.optim.AdamW.step + zero_grad (train.py:325-326).
 #pragma once
 #include <string>
+#include <cmath>
 #include "common.cuh"
 #include "k_step_fp32.cuh"
 #include "umma_ptx.cuh"
-#include "k_step_umma.cuh"      // column maps, weight-image layout, PE ladders, packed-half helpers (namespace um)
+#include "k_umma_image.cuh"     // column maps, weight-image layout, PE ladders, packed-half helpers (namespace um)
 
 // Optional cycle trace (profiling builds only: -DVMB_TRACE), same buffer as the round-1 kernel
 #ifdef VMB_TRACE
 #define TRF(row, slot) do { if (blockIdx.x == 0 && (slot) < 256) g_vmb_trace[row][slot] = clock64(); } while (0)
 #else
 #define TRF(row, slot) do { } while (0)
+#endif
+// finer stamps inside the PE-forward phase of group 0 (row 2), profiling builds with -DVMB_TRACE -DVMB_TRACE_E0
+#if defined(VMB_TRACE) && defined(VMB_TRACE_E0)
+#define TRE() do { if (tid == 0) { TRF(2, tre); ++tre; } } while (0)
+#else
+#define TRE() do { } while (0)
 #endif
 
 struct FusedExtra {
@@ -269,15 +286,23 @@ struct Issuer {
   }
 };
 
-// global tile -> owning CTA of the static partition [T c / G, T (c+1) / G)
-__device__ __forceinline__ int cta_of_tile(long long t, long long T, int G) { return (int)(((t + 1) * G - 1) / T); }
+// Work partition: CTA c owns tile pairs [begin[c], begin[c+1]) of the global list (object-major).  Built on the host
+// (fused_partition) so that a CTA whose range crosses an object boundary -- it pays a second flush / weight load /
+// pipeline fill -- gets correspondingly fewer pairs: no CTA's cost exceeds the even share by more than one pair.
+constexpr int MAX_CTAS = 192;
+struct Ranges { int begin[MAX_CTAS + 1]; };
+__device__ __forceinline__ int cta_of_pair(const Ranges& rg, int G, int pair) {        // largest c with begin[c] <= pair
+  int lo = 0, hi = G - 1;
+  while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (rg.begin[mid] <= pair) lo = mid; else hi = mid - 1; }
+  return lo;
+}
 
 }  // namespace uf
 
 // ---------------------------------------------------------------------------------------------------------------
 template <int SC>
 __global__ void __launch_bounds__(uf::NT, 1)
-k_step_fused(StepParams a, FusedExtra x, VmbLayout L, const unsigned char* image, int tpo, int npo, int nr, int rpw, long long T) {
+k_step_fused(StepParams a, FusedExtra x, VmbLayout L, const unsigned char* image, const __grid_constant__ uf::Ranges rg, int tpo, int npo, int nr, int rpw) {
   using namespace uf;
   extern __shared__ __align__(1024) unsigned char smem[];
   Misc* misc = reinterpret_cast<Misc*>(smem + SM_MISC);
@@ -295,7 +320,7 @@ k_step_fused(StepParams a, FusedExtra x, VmbLayout L, const unsigned char* image
   }
   if (warp == 15) { ptx::tmem_alloc(&misc->tmem_base, 512); ptx::tmem_relinquish(); }
   const int G = gridDim.x;
-  const long long gt_begin = (T * blockIdx.x) / G, gt_end = (T * (blockIdx.x + 1)) / G;
+  const long long gt_begin = rg.begin[blockIdx.x], gt_end = rg.begin[blockIdx.x + 1];
   __syncthreads();
   if (tid == 0 && gt_begin < gt_end) {     // first object's weight image: in flight while the mask counts run
     ptx::mbar_arrive_expect_tx(&misc->wbar, um::IMG_BYTES);
@@ -410,7 +435,7 @@ k_step_fused(StepParams a, FusedExtra x, VmbLayout L, const unsigned char* image
   // apply AdamW (fuse_adam) or add the reduced gradient into `grads`.  `owner` writes the object's loss terms / status.
   // Called by all threads of the CTA; returns the object's skip flag (loss explosion guard, render_rays.py:88-90).
   auto finish_rows = [&](int b, int i_lo, int i_hi, bool owner) -> int {
-    const int c_first = cta_of_tile((long long)b * npo, T, G), c_last = cta_of_tile((long long)(b + 1) * npo - 1, T, G);
+    const int c_first = cta_of_pair(rg, G, b * npo), c_last = cta_of_pair(rg, G, (b + 1) * npo - 1);
     const int nseg = c_last - c_first + 1;
     const int i_sl = owner ? 0 : 1;
     {
@@ -516,8 +541,8 @@ k_step_fused(StepParams a, FusedExtra x, VmbLayout L, const unsigned char* image
   };
 
   // The work list is in units of TILE PAIRS (the two point groups of a CTA advance in lock-step rounds, one tile each):
-  // CTA c owns pairs [T c / G, T (c+1) / G), every segment of an object is a whole number of rounds and no CTA runs more
-  // than ceil(T / G) rounds -- with a per-tile split a segment boundary inside a CTA cost it an extra round.
+  // every segment of an object is a whole number of rounds -- with a per-tile split a segment boundary inside a CTA
+  // cost it an extra round.
   for (long long gt = gt_begin; gt < gt_end;) {
     const int b = (int)(gt / npo);
     const int p0 = (int)(gt - (long long)b * npo);
@@ -639,20 +664,24 @@ k_step_fused(StepParams a, FusedExtra x, VmbLayout L, const unsigned char* image
       TRG();                                            // tile start
       // ---- E0: positional embedding (embedding.py:82-91) ----------------------------------------------------
       const float t0x = nx * isc, t1x = ny * isc, t2x = nz * isc, zv = nzv;
+      const uint64_t tp0 = um::pk2(t0x, t0x), tp1 = um::pk2(t1x, t1x), tp2 = um::pk2(t2x, t2x);
       const float gd = n_gd, gc0 = n_c0, gc1 = n_c1, gc2 = n_c2;
       const int smv = n_sm;
+      [[maybe_unused]] int tre = 16 * ((t - t_first) / t_step);
+      TRE();
       prefetch(t + t_step);
+      TRE();
       {
         uint4* e1 = reinterpret_cast<uint4*>(act + FG_E1 * FGB + p * 16);
         uint4* e2 = reinterpret_cast<uint4*>(act + FG_E2 * FGB + p * 16);
         const int q0 = hsel ? 3 : 0, q1 = hsel ? 5 : 3;
 #pragma unroll 1
         for (int q = q0; q < q1; ++q) {                // directions 4q .. 4q+3
-          const float* bq = Bd + q * 12;
-          float pj[4], sv[4][6];
-#pragma unroll
-          for (int dd = 0; dd < 4; ++dd) pj[dd] = fmaf(bq[dd * 3 + 2], t2x, fmaf(bq[dd * 3 + 1], t1x, bq[dd * 3] * t0x));
-          um::sin_ladder4(pj, sv);
+          float sv[4][6];
+          uint64_t pj01, pj23;
+          um::project4(Bd, q, tp0, tp1, tp2, pj01, pj23);
+          um::sin_ladder4_x2(pj01, pj23, sv);
+          TRE();
           if (q == q0 && wb_pending) {                  // the previous tile's deferred MMAs still read E1 / DPR / FC3
             um::mbar_wait_or_trap(&misc->wb[g], wph); wph ^= 1; wb_pending = false;
           }
@@ -665,11 +694,12 @@ k_step_fused(StepParams a, FusedExtra x, VmbLayout L, const unsigned char* image
             ptx::tmem_st4(tA + TC_E1A + (2 * q + 2) * 4, ub.x, ub.y, ub.z, ub.w);
             ptx::tmem_st4(tA + TC_E2A + q * 4, uc.x, uc.y, uc.z, uc.w);
           }
+          TRE();
         }
         if (hsel) {
           // direction 20 shares chunk 0 of emb1 with [1, x, y, z] and chunk 5 of emb2 with the const-1 column
           float s[6];
-          um::sin_ladder(fmaf(Bd[62], t2x, fmaf(Bd[61], t1x, Bd[60] * t0x)), s);
+          um::sin_ladder(fmaf(Bd[2 * um::DIRS_PITCH + 20], t2x, fmaf(Bd[um::DIRS_PITCH + 20], t1x, Bd[20] * t0x)), s);
           const uint4 u0 = make_uint4(um::pack_h2(1.0f, t0x), um::pack_h2(t1x, t2x), um::pack_h2(s[0], s[1]), um::pack_h2(s[2], s[3]));
           const uint4 u5 = make_uint4(um::pack_h2(s[4], s[5]), um::pack_h2(1.0f, 0.f), 0u, 0u);
           e1[0] = u0;
@@ -814,11 +844,10 @@ k_step_fused(StepParams a, FusedExtra x, VmbLayout L, const unsigned char* image
           um::tmem_ld8(tE + 16 * q + 8, g1a);          // emb1 cols of directions 4q, 4q+1 (k = 0..3)
           um::tmem_ld8(tE + 16 * q + 16, g1b);         //                          4q+2, 4q+3
           um::tmem_ld8(tA + 8 * q, g2);                // emb2 cols (k = 4, 5)
-          const float* bq = Bd + q * 12;
-          float pj[4], cv[4][6], dp[4];
-#pragma unroll
-          for (int dd = 0; dd < 4; ++dd) pj[dd] = fmaf(bq[dd * 3 + 2], t2x, fmaf(bq[dd * 3 + 1], t1x, bq[dd * 3] * t0x));
-          um::cos_ladder4(pj, cv);
+          float cv[4][6], dp[4];
+          uint64_t pj01, pj23;
+          um::project4(Bd, q, tp0, tp1, tp2, pj01, pj23);
+          um::cos_ladder4_x2(pj01, pj23, cv);
           ptx::tmem_ld_wait();
 #pragma unroll
           for (int dd = 0; dd < 4; ++dd) {
@@ -839,7 +868,7 @@ k_step_fused(StepParams a, FusedExtra x, VmbLayout L, const unsigned char* image
           float g1[8], g2[8], c[6];
           um::tmem_ld8(tE, g1);
           um::tmem_ld8(tA + 40, g2);
-          um::cos_ladder(fmaf(Bd[62], t2x, fmaf(Bd[61], t1x, Bd[60] * t0x)), c);
+          um::cos_ladder(fmaf(Bd[2 * um::DIRS_PITCH + 20], t2x, fmaf(Bd[um::DIRS_PITCH + 20], t1x, Bd[20] * t0x)), c);
           ptx::tmem_ld_wait();
           float d = g1[4] * c[0];
           d = fmaf(2.f * g1[5], c[1], d); d = fmaf(4.f * g1[6], c[2], d); d = fmaf(8.f * g1[7], c[3], d);
@@ -885,7 +914,9 @@ k_step_fused(StepParams a, FusedExtra x, VmbLayout L, const unsigned char* image
       ptx::mbar_arrive_expect_tx(&misc->wbar, um::IMG_BYTES);        // the next object's image lands during the flush
       ptx::bulk_g2s(smem + SM_W, image + (size_t)(gt / npo) * um::IMG_BYTES, um::IMG_BYTES, &misc->wbar);
     }
-    float* Pr = x.partials + (size_t)(blockIdx.x + b) * L.stride;
+    // the segment's gradient row is assembled in shared memory (group 0's activation region is idle now: the scattered
+    // 4-byte stores of the accumulator -> parameter-index mapping cost nothing there) and leaves as coalesced 16-byte stores
+    float* Pr = reinterpret_cast<float*>(smem + SM_ACT0);
     if (tid < 3) {                                      // fixed summation order -> reproducible loss terms
       float s = 0.f;
 #pragma unroll
@@ -930,13 +961,19 @@ k_step_fused(StepParams a, FusedExtra x, VmbLayout L, const unsigned char* image
       }
       ptx::tmem_st_wait();
     }
+    __syncthreads();
+    {
+      float4* dst = reinterpret_cast<float4*>(x.partials + (size_t)(blockIdx.x + b) * L.stride);
+      const float4* src = reinterpret_cast<const float4*>(Pr);
+      for (int i = tid; i < (L.stride >> 2); i += NT) dst[i] = src[i];
+    }
     // ---- reduce + update ---------------------------------------------------------------------------------------------
     // cooperative launch: after the LAST segment (below, outside this loop), all CTAs share the reduction of all objects.
     // otherwise: the last segment of the object to arrive reduces that object's rows here.
     if (!x.cooperative) {
       __threadfence();
       __syncthreads();
-      const int c_first = cta_of_tile((long long)b * npo, T, G), c_last = cta_of_tile((long long)(b + 1) * npo - 1, T, G);
+      const int c_first = cta_of_pair(rg, G, b * npo), c_last = cta_of_pair(rg, G, (b + 1) * npo - 1);
       if (tid == 0) misc->fin = (atomicAdd(&x.obj_done[b], 1u) + 1u == (unsigned int)(c_last - c_first + 1)) ? 1 : 0;
       __syncthreads();
       if (misc->fin) {
@@ -1000,6 +1037,34 @@ k_step_fused(StepParams a, FusedExtra x, VmbLayout L, const unsigned char* image
 // ---------------------------------------------------------------------------------------------------------------
 static int fused_rows_needed(int n_obj, int n_sm) { return n_obj + n_sm; }
 
+// Cost-aware split of B objects x npo tile pairs over G CTAs.  Starting a second object inside a CTA costs it a flush
+// of the gradient partial, a weight load and a pipeline refill (~0.4 of a round measured), so pairs are laid out on a
+// virtual axis x(p) = p + beta * (object of p) -- every object boundary is a gap of beta -- and that axis is split
+// evenly: a CTA whose range crosses a boundary gets correspondingly fewer pairs.  beta is the largest of {1, 0.7, 0.4, 0}
+// that does not raise the maximum number of rounds per CTA.
+static void fused_partition(int B, int npo, int G, uf::Ranges& rg) {
+  const long long T = (long long)B * npo;
+  double beta = 0.0;
+  if (T >= 2LL * G) {
+    const long long rounds = (T + G - 1) / G;
+    for (double cand : {1.0, 0.7, 0.4}) {
+      if ((long long)std::ceil(((double)T + cand * (B - 1)) / G - 1e-9) <= rounds) { beta = cand; break; }
+    }
+  }
+  const double V = (double)T + beta * (B - 1);
+  int c = 0;
+  rg.begin[0] = 0;
+  for (long long p = 0; p < T; ++p) {
+    const double x = (double)p + beta * (double)(p / npo);
+    while (c < G - 1 && x >= V * (c + 1) / G && p > rg.begin[c] && T - p >= G - 1 - c) rg.begin[++c] = (int)p;
+    if (T - p - 1 == G - 1 - c && c < G - 1) {            // one pair left per remaining CTA
+      for (long long q = p + 1; q < T; ++q) rg.begin[++c] = (int)q;
+      break;
+    }
+  }
+  while (c < G) rg.begin[++c] = (int)T;
+}
+
 static int fused_launch_step(const VmbLayout& L, const StepParams& sp, const FusedExtra& fx, const void* image, int n_sm,
                              cudaStream_t st, std::string& err) {
   using namespace uf;
@@ -1022,9 +1087,13 @@ static int fused_launch_step(const VmbLayout& L, const StepParams& sp, const Fus
   const int tpo = (sp.R + nr - 1) / nr;       // tiles per object
   const int npo = (tpo + 1) / 2;              // rounds (tile pairs) per object
   const long long T = (long long)npo * sp.B;
+  if (T > 0x7fffffffLL) { err = "fused step kernel: too many tiles"; return -1; }
   long long grid = T;
   if (grid > n_sm) grid = n_sm;
+  if (grid > MAX_CTAS) grid = MAX_CTAS;
   if (grid < 1) grid = 1;
+  Ranges rg;
+  fused_partition(sp.B, npo, (int)grid, rg);
   const unsigned char* img = (const unsigned char*)image;
   FusedExtra fxl = fx;
   // every CTA is resident (grid <= #SMs, one CTA per SM) -- the cooperative attribute makes the runtime guarantee it,
@@ -1044,9 +1113,9 @@ static int fused_launch_step(const VmbLayout& L, const StepParams& sp, const Fus
   attr[0].val.cooperative = fxl.cooperative;
   cfg.attrs = attr; cfg.numAttrs = 1;
   cudaError_t e;
-  if (sp.S == 10)      e = cudaLaunchKernelEx(&cfg, k_step_fused<10>, sp, fxl, L, img, tpo, npo, nr, rpw, T);
-  else if (sp.S == 14) e = cudaLaunchKernelEx(&cfg, k_step_fused<14>, sp, fxl, L, img, tpo, npo, nr, rpw, T);
-  else                 e = cudaLaunchKernelEx(&cfg, k_step_fused<0>, sp, fxl, L, img, tpo, npo, nr, rpw, T);
+  if (sp.S == 10)      e = cudaLaunchKernelEx(&cfg, k_step_fused<10>, sp, fxl, L, img, rg, tpo, npo, nr, rpw);
+  else if (sp.S == 14) e = cudaLaunchKernelEx(&cfg, k_step_fused<14>, sp, fxl, L, img, rg, tpo, npo, nr, rpw);
+  else                 e = cudaLaunchKernelEx(&cfg, k_step_fused<0>, sp, fxl, L, img, rg, tpo, npo, nr, rpw);
   if (e == cudaSuccess) e = cudaGetLastError();
   if (e != cudaSuccess) { err = std::string("k_step_fused launch: ") + cudaGetErrorString(e); return -2; }
   return 0;

@@ -12,7 +12,7 @@
 #include "k_adam.cuh"
 #include "k_sampler.cuh"
 #include "k_ingest.cuh"
-#include "k_step_umma.cuh"
+#include "k_umma_image.cuh"
 #include "k_step_fused.cuh"
 #include "k_gemm_umma.cuh"
 #include "k_layerwise.cuh"
@@ -203,12 +203,6 @@ static int fused_scratch(vmb_handle* h, cudaStream_t st) {
   return VMB_OK;
 }
 
-static bool use_v6_kernel() {      // VMB_K1=v6: the round-1 kernel chain (K0 + k_step_umma + atomics + K2), kept for A/B timing
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("VMB_K1"); v = (e && !strcmp(e, "v6")) ? 1 : 0; }
-  return v == 1;
-}
-
 // VMB_DETERMINISTIC=1: one point group per CTA walks the tiles, so every wgrad accumulator receives ONE in-order stream
 // of MMAs and the step is bitwise reproducible (default: two groups interleave their MMAs in arrival order -- still no
 // floating-point atomics, but the fp32 summation order of the two tile streams inside an SM varies from run to run)
@@ -275,7 +269,7 @@ int vmb_step(vmb_handle* h, const vmb_step_args* a, void* stream) {
   };
 
   // ---- hidden 32: ONE launch (counts + step + ordered gradient reduction (+ AdamW)) ----------------------------
-  if (impl == VMB_IMPL_UMMA && !use_v6_kernel()) {
+  if (impl == VMB_IMPL_UMMA) {
     if (!umma_possible) return fail(h, VMB_E_UNSUPPORTED, "vmb_step: tensor-core path needs hidden=32, n_freq=6 and an image");
     const int rc0 = fused_scratch(h, st);
     if (rc0 != VMB_OK) return rc0;
@@ -317,13 +311,7 @@ int vmb_step(vmb_handle* h, const vmb_step_args* a, void* stream) {
   {
     EvGuard evg{(cudaEvent_t)a->k1_stop_event, st};
     if (a->k1_start_event) cudaEventRecord((cudaEvent_t)a->k1_start_event, st);
-    if (impl == VMB_IMPL_UMMA) {
-      if (!umma_possible || a->n_samples > UMMA_MAX_S)
-        return fail(h, VMB_E_UNSUPPORTED, "vmb_step: round-1 UMMA kernel needs hidden=32, n_freq=6, an image and S<=16");
-      std::string err;
-      rc = umma_launch_step(h->L, sp, a->image, st, err);
-      if (rc != VMB_OK) return fail(h, rc, err);
-    } else if (impl == VMB_IMPL_LAYERWISE) {
+    if (impl == VMB_IMPL_LAYERWISE) {
       if (!lw_possible) return fail(h, VMB_E_UNSUPPORTED, "vmb_step: layer-wise path needs hidden 64/128/256, n_freq=6 and an image");
       std::string err;
       rc = lw::launch_step(h->ws, h->L, sp, a->image, st, err);
@@ -359,8 +347,7 @@ int vmb_forward(vmb_handle* h, const vmb_forward_args* a, void* stream) {
     std::string err;
     FusedExtra fx;
     memset(&fx, 0, sizeof(fx));
-    const int rc = use_v6_kernel() ? umma_launch_step(h->L, sp, a->image, (cudaStream_t)stream, err)
-                                   : fused_launch_step(h->L, sp, fx, a->image, h->n_sm, (cudaStream_t)stream, err);
+    const int rc = fused_launch_step(h->L, sp, fx, a->image, h->n_sm, (cudaStream_t)stream, err);
     if (rc) return fail(h, rc == -4 ? VMB_E_UNSUPPORTED : VMB_E_CUDA, err);
     return VMB_OK;
   }
