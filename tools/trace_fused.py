@@ -56,3 +56,10 @@ if os.environ.get("TRACE_E0"):
             break
         d = np.diff(seg[seg != 0])
         print(f"tile {tile}: prefetch issue, [ladder, stores(+wait on the previous tile's deferred MMAs at iteration 0)] x3:", d.tolist())
+names2 = {210: "barriers initialised", 211: "TMEM allocated + first weight copy issued", 212: "own mask counts done", 213: "all counts done (sync)",
+          200: "wgrad accumulators zeroed (setup done)", 201: "first weights landed", 202: "last segment's tiles done", 203: "its gradient row flushed",
+          205: "grid barrier passed", 206: "finish: start", 207: "finish: slices reduced + updated", 208: "finish: fenced", 204: "kernel end"}
+print("prologue / epilogue detail (cycles from kernel entry):")
+for k in (210, 211, 212, 213, 200, 201, 202, 203, 205, 206, 207, 208, 204):
+    if t[k]:
+        print(f"  {names2[k]:48s} {int(t[k] - t[199])}")

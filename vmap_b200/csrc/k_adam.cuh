@@ -25,6 +25,7 @@ struct AdamParams {
   int* step_counter; unsigned int* ticket;
   double lr, b1, b2d;
   float log_b1, log_b2;       // ln(beta1), ln(beta2)
+  const float2* bc_table; int bc_n;   // [t] -> (1 - beta1^t, sqrt(1 - beta2^t)), host-built in double precision
 };
 
 __global__ void __launch_bounds__(256) k_adamw(AdamParams a) {
@@ -45,10 +46,17 @@ __global__ void __launch_bounds__(256) k_adamw(AdamParams a) {
   if (threadIdx.x < 2) {
     const int rb = row0 + threadIdx.x;
     if (a.step_counter && rb < a.B) {
-      // 1 - beta^t = -expm1(t ln beta), fp32, cancellation-free (<= 3e-7 relative to torch's double scalars)
-      const float t = (float)(a.step_counter[rb] + 1);
-      s_step_size[threadIdx.x] = (float)a.lr / (-expm1f(t * a.log_b1));
-      s_bc2_sqrt[threadIdx.x] = sqrtf(-expm1f(t * a.log_b2));
+      // bias corrections of step t from the host-built table (torch's double scalars, rounded once); beyond the table
+      // 1 - beta^t = -expm1(t ln beta), fp32, cancellation-free (<= 3e-7 relative)
+      const int t = a.step_counter[rb] + 1;
+      if (t < a.bc_n) {
+        const float2 bc = a.bc_table[t];
+        s_step_size[threadIdx.x] = (float)a.lr / bc.x;
+        s_bc2_sqrt[threadIdx.x] = bc.y;
+      } else {
+        s_step_size[threadIdx.x] = (float)a.lr / (-expm1f((float)t * a.log_b1));
+        s_bc2_sqrt[threadIdx.x] = sqrtf(-expm1f((float)t * a.log_b2));
+      }
     } else {
       s_step_size[threadIdx.x] = a.step_size; s_bc2_sqrt[threadIdx.x] = a.bc2_sqrt;
     }

@@ -55,6 +55,7 @@ struct FusedExtra {
   float* partials;            // [(B + grid)][stride] per-(CTA, object) gradient partials, row = blockIdx + object
   unsigned int* obj_done;     // [B] segments finished per object (non-cooperative), [B] skip flags, [2] grid arrive / depart (self-resetting)
   const int* counts_in;       // optional [B][4] external mask counts (ray-sharded iMAP: all-reduced by the caller)
+  int* counts_pub;            // [B][4] scratch: cooperative launches count each object ONCE (CTA b mod grid) and publish here
   int fuse_adam;              // 1: the finisher applies AdamW; 0: it adds the reduced gradient into `grads`
   float* p; float* m; float* v;
   __half* image_out; const int* img_index; int img_halves;
@@ -62,6 +63,8 @@ struct FusedExtra {
   float step_size, bc2_sqrt;  // host-computed bias corrections when step_counter == nullptr
   double lr, b1d, b2d;
   float log_b1, log_b2;       // ln(beta1), ln(beta2)
+  const float2* bc_table;     // [bc_n] (1 - beta1^t, sqrt(1 - beta2^t)) built on the host in double precision, t = index
+  int bc_n;
   float lr_wd, one_m_b1, b2, one_m_b2, eps;
   int guard_loss;
   int* status;
@@ -319,6 +322,7 @@ k_step_fused(StepParams a, FusedExtra x, VmbLayout L, const unsigned char* image
     ptx::mbar_init_fence();
   }
   if (warp == 15) { ptx::tmem_alloc(&misc->tmem_base, 512); ptx::tmem_relinquish(); }
+  if (tid == 0) TRF(3, 210);          // barriers initialised
   const int G = gridDim.x;
   const long long gt_begin = rg.begin[blockIdx.x], gt_end = rg.begin[blockIdx.x + 1];
   __syncthreads();
@@ -326,8 +330,50 @@ k_step_fused(StepParams a, FusedExtra x, VmbLayout L, const unsigned char* image
     ptx::mbar_arrive_expect_tx(&misc->wbar, um::IMG_BYTES);
     ptx::bulk_g2s(smem + SM_W, image + (size_t)(gt_begin / npo) * um::IMG_BYTES, um::IMG_BYTES, &misc->wbar);
   }
-  // ---- K0 in the prologue: mask counts of EVERY object (the any-empty early-out couples them, render_rays.py:68-73)
-  if (!a.fwd_only) {
+  if (tid == 0) TRF(3, 211);          // TMEM allocated (first __syncthreads passed), first weight copy issued
+  // ---- K0 in the prologue: mask counts of EVERY object (the any-empty early-out couples them, render_rays.py:68-73).
+  // Cooperative launch: CTA c counts objects c, c + grid, ... ONCE and publishes counts + empty flags + a "published"
+  // counter in global memory; every CTA starts its tiles at once and acquires the counts right before its first
+  // volume render (thousands of cycles later: the wait is free).  Otherwise every CTA counts everything (148-fold
+  // redundant reads of the label / mask bytes: ~3 us of L2 traffic on the launch's critical path).
+  const bool pub_counts = x.cooperative && !x.counts_in && !a.fwd_only;
+  unsigned int* gbar = x.obj_done + 2 * a.B;            // [0] arrive, [1] depart, [2] objects published, [3..5] empty flags
+  if (pub_counts) {
+    for (int b = blockIdx.x; b < a.B; b += G) {
+      if (tid < 3) cnt[tid] = 0;
+      __syncthreads();
+      const unsigned char* s = a.sem + (size_t)b * a.sem_stride;
+      const unsigned char* m = a.mask + (size_t)b * a.mask_stride;
+      const bool vec = (((size_t)s | (size_t)m) & 3) == 0;
+      const int nw = vec ? (R >> 2) : 0;
+      auto nzb = [](uint32_t v) { v |= v >> 4; v |= v >> 2; v |= v >> 1; return v & 0x01010101u; };
+      int nd = 0, no = 0, ns = 0;
+      for (int w = tid; w < nw; w += NT) {               // four rays per 32-bit load
+        const uint32_t sv = __ldg(reinterpret_cast<const uint32_t*>(s) + w), mv = __ldg(reinterpret_cast<const uint32_t*>(m) + w);
+        const uint32_t o = nzb(sv);
+        no += __popc(o); nd += __popc(o & nzb(mv)); ns += __popc(nzb(sv ^ 0x02020202u));
+      }
+      for (int r = (nw << 2) + tid; r < R; r += NT) {
+        const int sv = s[r], mo = sv != 0;
+        nd += (m[r] != 0) & mo; no += mo; ns += sv != 2;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        nd += __shfl_xor_sync(0xffffffffu, nd, o); no += __shfl_xor_sync(0xffffffffu, no, o); ns += __shfl_xor_sync(0xffffffffu, ns, o);
+      }
+      if (lane == 0) { atomicAdd(&cnt[0], nd); atomicAdd(&cnt[1], no); atomicAdd(&cnt[2], ns); }
+      __syncthreads();
+      if (tid == 0) {
+        for (int k = 0; k < 3; ++k) {
+          x.counts_pub[b * 4 + k] = cnt[k];
+          if (cnt[k] == 0) atomicOr(&gbar[3 + k], 1u);
+        }
+        __threadfence();
+        atomicAdd(&gbar[2], 1u);
+      }
+      __syncthreads();
+    }
+  } else if (!a.fwd_only) {
     if (x.counts_in) {
       for (int i = tid; i < a.B * 3; i += NT) {
         const int c = x.counts_in[(i / 3) * 4 + (i % 3)];
@@ -357,9 +403,13 @@ k_step_fused(StepParams a, FusedExtra x, VmbLayout L, const unsigned char* image
           if (ns == 0) misc->on[2] = 0;
         }
       };
-      for (int bA = warp; bA < a.B; bA += 2 * (NT / 32)) {
-        const int bB = bA + NT / 32;
-        const bool hasB = bB < a.B;
+      // every CTA needs every object's counts: each starts at a different object, so the grid does not hit the same
+      // cache lines at the same moment
+      const int shift = (int)((blockIdx.x * 7u) % (unsigned)a.B);
+      for (int iA = warp; iA < a.B; iA += 2 * (NT / 32)) {
+        const int iB = iA + NT / 32;
+        const bool hasB = iB < a.B;
+        const int bA = (iA + shift) % a.B, bB = hasB ? (iB + shift) % a.B : bA;
         const uint32_t* sA = reinterpret_cast<const uint32_t*>(a.sem + (size_t)bA * a.sem_stride);
         const uint32_t* mA = reinterpret_cast<const uint32_t*>(a.mask + (size_t)bA * a.mask_stride);
         const uint32_t* sB = reinterpret_cast<const uint32_t*>(a.sem + (size_t)(hasB ? bB : bA) * a.sem_stride);
@@ -375,15 +425,14 @@ k_step_fused(StepParams a, FusedExtra x, VmbLayout L, const unsigned char* image
             sa[u] = (in && vA) ? __ldg(sA + w) : 0u;  ma[u] = (in && vA) ? __ldg(mA + w) : 0u;
             sb[u] = (in && vB) ? __ldg(sB + w) : 0u;  mb[u] = (in && vB) ? __ldg(mB + w) : 0u;
           }
+          // one bit per byte: nonzero(x) folds a byte's bits into bit 0 (labels are 0 / 1 / 2, masks any nonzero = true)
+          auto nzb = [](uint32_t v) { v |= v >> 4; v |= v >> 2; v |= v >> 1; return v & 0x01010101u; };
 #pragma unroll
           for (int u = 0; u < 10; ++u) {
-            const int w = w0 + u * 32 + lane;
-            if (w < nw) {
-              uint32_t so = __vcmpne4(sa[u], 0u), s2 = __vcmpne4(sa[u], 0x02020202u), mo = __vcmpne4(ma[u], 0u);
-              if (vA) { cA[1] += __popc(so) >> 3; cA[2] += __popc(s2) >> 3; cA[0] += __popc(so & mo) >> 3; }
-              so = __vcmpne4(sb[u], 0u); s2 = __vcmpne4(sb[u], 0x02020202u); mo = __vcmpne4(mb[u], 0u);
-              if (vB) { cB[1] += __popc(so) >> 3; cB[2] += __popc(s2) >> 3; cB[0] += __popc(so & mo) >> 3; }
-            }
+            const bool in = w0 + u * 32 + lane < nw;
+            const uint32_t oa = (in && vA) ? nzb(sa[u]) : 0u, ob = (in && vB) ? nzb(sb[u]) : 0u;
+            cA[1] += __popc(oa); cA[0] += __popc(oa & nzb(ma[u])); cA[2] += (in && vA) ? __popc(nzb(sa[u] ^ 0x02020202u)) : 0;
+            cB[1] += __popc(ob); cB[0] += __popc(ob & nzb(mb[u])); cB[2] += (in && vB) ? __popc(nzb(sb[u] ^ 0x02020202u)) : 0;
           }
         }
         finish(bA, cA[0], cA[1], cA[2]);
@@ -391,9 +440,11 @@ k_step_fused(StepParams a, FusedExtra x, VmbLayout L, const unsigned char* image
       }
     }
   }
+  if (tid == 0) TRF(3, 212);          // this warp's mask counts done
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
+  if (tid == 0) TRF(3, 213);          // all counts done
   const uint32_t tm = misc->tmem_base;
   if (warp < 8) {                     // zero the persistent wgrad accumulators (192 columns x 128 lanes)
     const uint32_t zb = tm + ((uint32_t)((warp & 3) * 32) << 16) + (warp >> 2) * 96;
@@ -429,7 +480,10 @@ k_step_fused(StepParams a, FusedExtra x, VmbLayout L, const unsigned char* image
   is.tm = tm;
   is.acc = tm + ACC0 + g * ACC_STRIDE;
   const bool issuer_warp = (warp & 7) == 0;
+  // loss weights of this thread's current object: (term enabled: no object has an empty mask) / (this object's mask count)
   const float on_d = misc->on[0] ? 1.f : 0.f, on_c = misc->on[1] ? 1.f : 0.f, on_o = misc->on[2] ? 1.f : 0.f;
+  float w_d = 0.f, w_c = 0.f, w_o = 0.f;
+  bool cnt_ready = !pub_counts;       // published counts acquired?
 
   // Reduce object b's partial rows over float4 columns [i_lo, i_hi) in segment order (the same sum every run) and either
   // apply AdamW (fuse_adam) or add the reduced gradient into `grads`.  `owner` writes the object's loss terms / status.
@@ -437,105 +491,106 @@ k_step_fused(StepParams a, FusedExtra x, VmbLayout L, const unsigned char* image
   auto finish_rows = [&](int b, int i_lo, int i_hi, bool owner) -> int {
     const int c_first = cta_of_pair(rg, G, b * npo), c_last = cta_of_pair(rg, G, (b + 1) * npo - 1);
     const int nseg = c_last - c_first + 1;
-    const int i_sl = owner ? 0 : 1;
-    {
-      const float* P0 = x.partials + (size_t)(c_first + b) * L.stride;
-      if (warp == 0) {
-        // the segments' loss terms: up to ten segments are loaded by 30 lanes at once, then added in segment order
-        float s = 0.f;
-        if (nseg <= 10) {
-          const int k = lane / 3, j = lane - 3 * k;
-          const float v = (k < nseg) ? __ldcg(P0 + (size_t)k * L.stride + L.P + j) : 0.f;
-          for (int kk = 0; kk < nseg; ++kk) s += __shfl_sync(0xffffffffu, v, kk * 3 + (lane < 3 ? lane : 0));
-        } else if (lane < 3) {
-          for (int k = 0; k < nseg; ++k) s += __ldcg(P0 + (size_t)k * L.stride + L.P + lane);
-        }
-        const float l_d = __shfl_sync(0xffffffffu, s, 0), l_c = __shfl_sync(0xffffffffu, s, 1), l_o = __shfl_sync(0xffffffffu, s, 2);
-        if (lane == 0) {
-          const float tot = l_d + a.cs * l_c + a.os * l_o;
-          if (i_sl == 0) { float* lt = a.loss_terms + b * 4; lt[0] = l_d; lt[1] = l_c; lt[2] = l_o; lt[3] = tot; }
-          int bad = 0;                                  // render_rays.py:88-90: the reference aborts before the update
-          if (x.guard_loss) {
-            if (l_d > 100000.f || l_c > 100000.f || l_o > 100000.f) bad |= 1;
-            if (!(tot == tot) || fabsf(tot) > 3.0e38f) bad |= 2;
-            if (bad && x.status && i_sl == 0) atomicOr(x.status, bad);
-          }
-          misc->skip = bad;
-          if (x.fuse_adam && x.step_counter) {
-            // bias corrections 1 - beta^t = -expm1(t log beta): fp32 with the cancellation-free form (<= 3e-7 relative
-            // to torch's double-precision scalars), instead of two double-precision pow calls on the kernel's tail
-            const float t = (float)(x.step_counter[b] + 1);
-            misc->step_size = (float)x.lr / (-expm1f(t * x.log_b1));
-            misc->bc2_sqrt = sqrtf(-expm1f(t * x.log_b2));
-          } else {
-            misc->step_size = x.step_size; misc->bc2_sqrt = x.bc2_sqrt;
-          }
-        }
+    const float* P0 = x.partials + (size_t)(c_first + b) * L.stride;
+    const size_t row = (size_t)b * L.stride;
+    const int n4 = L.stride >> 2;
+    const bool upd = a.backward != 0;
+    // (1) the object's loss terms (segment order), the explosion guard and the bias corrections
+    if (warp == 0) {
+      float s = 0.f;
+      if (nseg <= 10) {                                 // up to ten segments are loaded by 30 lanes at once
+        const int k = lane / 3, j = lane - 3 * k;
+        const float v = (k < nseg) ? __ldcg(P0 + (size_t)k * L.stride + L.P + j) : 0.f;
+        for (int kk = 0; kk < nseg; ++kk) s += __shfl_sync(0xffffffffu, v, kk * 3 + (lane < 3 ? lane : 0));
+      } else if (lane < 3) {
+        for (int k = 0; k < nseg; ++k) s += __ldcg(P0 + (size_t)k * L.stride + L.P + lane);
       }
-      __syncthreads();
-      if (a.backward && !(misc->skip && x.fuse_adam)) {
-        const float step_size = misc->step_size, bc2_sqrt = misc->bc2_sqrt;
-        const size_t row = (size_t)b * L.stride;
-        const int n4 = L.stride >> 2;
-        for (int i4 = i_lo + tid; i4 < i_hi; i4 += NT) {
-          float4 gsum = make_float4(0.f, 0.f, 0.f, 0.f);
-          const float4* src = reinterpret_cast<const float4*>(P0) + i4;
-          // state loads first, then the partial rows eight at a time (all loads of a batch in flight together);
-          // the additions run in segment order = CTA order: the same sum every run
-          float4 pp = make_float4(0.f, 0.f, 0.f, 0.f), mm = pp, vv = pp;
-          if (x.fuse_adam) {
-            pp = *(reinterpret_cast<const float4*>(x.p + row) + i4);
-            mm = *(reinterpret_cast<const float4*>(x.m + row) + i4);
-            vv = *(reinterpret_cast<const float4*>(x.v + row) + i4);
+      const float l_d = __shfl_sync(0xffffffffu, s, 0), l_c = __shfl_sync(0xffffffffu, s, 1), l_o = __shfl_sync(0xffffffffu, s, 2);
+      if (lane == 0) {
+        const float tot = l_d + a.cs * l_c + a.os * l_o;
+        if (owner) { float* lt = a.loss_terms + b * 4; lt[0] = l_d; lt[1] = l_c; lt[2] = l_o; lt[3] = tot; }
+        int bad = 0;                                    // render_rays.py:88-90: the reference aborts before the update
+        if (x.guard_loss) {
+          if (l_d > 100000.f || l_c > 100000.f || l_o > 100000.f) bad |= 1;
+          if (!(tot == tot) || fabsf(tot) > 3.0e38f) bad |= 2;
+          if (bad && x.status && owner) atomicOr(x.status, bad);
+        }
+        misc->skip = bad;
+        if (x.fuse_adam && x.step_counter) {
+          // bias corrections of step t from the host-built table (torch's double-precision scalars, rounded once);
+          // beyond the table: 1 - beta^t = -expm1(t ln beta) in fp32 (cancellation-free, <= 3e-7 relative)
+          const int t = x.step_counter[b] + 1;
+          if (t < x.bc_n) {
+            const float2 bc = x.bc_table[t];
+            misc->step_size = (float)x.lr / bc.x;
+            misc->bc2_sqrt = bc.y;
+          } else {
+            misc->step_size = (float)x.lr / (-expm1f((float)t * x.log_b1));
+            misc->bc2_sqrt = sqrtf(-expm1f((float)t * x.log_b2));
           }
-          for (int k0 = 0; k0 < nseg; k0 += 8) {
-            float4 u[8];
-#pragma unroll
-            for (int k = 0; k < 8; ++k) u[k] = (k0 + k < nseg) ? __ldcg(src + (size_t)(k0 + k) * n4) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-            for (int k = 0; k < 8; ++k)
-              if (k0 + k < nseg) { gsum.x += u[k].x; gsum.y += u[k].y; gsum.z += u[k].z; gsum.w += u[k].w; }
-          }
-          const int e = i4 * 4;
-          if (!x.fuse_adam) {
-            float4* gd4 = reinterpret_cast<float4*>(a.grads + row) + i4;
-            float4 o = *gd4;
-            o.x += gsum.x; o.y += gsum.y; o.z += gsum.z; o.w += gsum.w;
-            if (e + 3 >= L.P) { if (e + 0 >= L.P) o.x = 0.f; if (e + 1 >= L.P) o.y = 0.f; if (e + 2 >= L.P) o.z = 0.f; o.w = 0.f; }
-            *gd4 = o;
-            continue;
-          }
-          // torch.optim.AdamW._single_tensor_adamw, op for op as k_adamw restates it
-          float* pj = &pp.x; float* mj = &mm.x; float* vj = &vv.x; const float* gj = &gsum.x;
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            if (e + j >= L.P) continue;
-            float pw = pj[j] * x.lr_wd;
-            const float m1 = mj[j] + (gj[j] - mj[j]) * x.one_m_b1;
-            const float v1 = vj[j] * x.b2 + (x.one_m_b2 * gj[j]) * gj[j];
-            const float denom = sqrtf(v1) / bc2_sqrt + x.eps;
-            pw = pw - step_size * (m1 / denom);
-            pj[j] = pw; mj[j] = m1; vj[j] = v1;
-          }
-          *(reinterpret_cast<float4*>(x.p + row) + i4) = pp;
-          *(reinterpret_cast<float4*>(x.m + row) + i4) = mm;
-          *(reinterpret_cast<float4*>(x.v + row) + i4) = vv;
-          if (x.image_out) {
-            __half* img = x.image_out + (size_t)b * x.img_halves;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              if (e + j < L.P) {
-                const int ti = x.img_index[e + j];
-                if (ti >= 0) img[ti] = __float2half_rn(pj[j]);
-                else if (ti <= -2) reinterpret_cast<float*>(img)[-(ti + 2)] = pj[j];
-              }
-            }
-          }
+        } else {
+          misc->step_size = x.step_size; misc->bc2_sqrt = x.bc2_sqrt;
         }
       }
     }
     __syncthreads();
     const int sk = misc->skip;
+    // (2) reduce + update this CTA's columns (normally at most one float4 column per thread).  Deliberately compact
+    //     code: it runs once per launch out of a cold instruction cache, where instruction fetch, not data, is the cost
+    if (upd && !(sk && x.fuse_adam)) {
+      const float step_size = misc->step_size, bc2_sqrt = misc->bc2_sqrt;
+      for (int c4 = i_lo + tid; c4 < i_hi; c4 += NT) {
+        const float4* src = reinterpret_cast<const float4*>(P0) + c4;
+        float4 pp, mm = make_float4(0.f, 0.f, 0.f, 0.f), vv = mm;
+        if (x.fuse_adam) {
+          pp = *(reinterpret_cast<const float4*>(x.p + row) + c4);
+          mm = *(reinterpret_cast<const float4*>(x.m + row) + c4);
+          vv = *(reinterpret_cast<const float4*>(x.v + row) + c4);
+        } else {
+          pp = *(reinterpret_cast<const float4*>(a.grads + row) + c4);
+        }
+        // segment order = CTA order: the same sum every run; four rows in flight per batch
+        float4 gsum = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 1
+        for (int k0 = 0; k0 < nseg; k0 += 4) {
+          float4 u[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) u[k] = (k0 + k < nseg) ? __ldcg(src + (size_t)(k0 + k) * n4) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            if (k0 + k < nseg) { gsum.x += u[k].x; gsum.y += u[k].y; gsum.z += u[k].z; gsum.w += u[k].w; }
+        }
+        const int e = c4 * 4;
+        if (!x.fuse_adam) {
+          float4 o = pp;
+          o.x += gsum.x; o.y += gsum.y; o.z += gsum.z; o.w += gsum.w;
+          if (e + 3 >= L.P) { if (e + 0 >= L.P) o.x = 0.f; if (e + 1 >= L.P) o.y = 0.f; if (e + 2 >= L.P) o.z = 0.f; o.w = 0.f; }
+          *(reinterpret_cast<float4*>(a.grads + row) + c4) = o;
+          continue;
+        }
+        // torch.optim.AdamW._single_tensor_adamw, op for op as k_adamw restates it
+        float* pj = &pp.x; float* mj = &mm.x; float* vj = &vv.x; const float* gj = &gsum.x;
+        __half* img = x.image_out ? x.image_out + (size_t)b * x.img_halves : nullptr;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (e + j >= L.P) continue;
+          float pw = pj[j] * x.lr_wd;
+          const float m1 = mj[j] + (gj[j] - mj[j]) * x.one_m_b1;
+          const float v1 = vj[j] * x.b2 + (x.one_m_b2 * gj[j]) * gj[j];
+          const float denom = sqrtf(v1) / bc2_sqrt + x.eps;
+          pw = pw - step_size * (m1 / denom);
+          pj[j] = pw; mj[j] = m1; vj[j] = v1;
+          if (img) {
+            const int t = x.img_index[e + j];
+            if (t >= 0) img[t] = __float2half_rn(pw);
+            else if (t <= -2) reinterpret_cast<float*>(img)[-(t + 2)] = pw;
+          }
+        }
+        *(reinterpret_cast<float4*>(x.p + row) + c4) = pp;
+        *(reinterpret_cast<float4*>(x.m + row) + c4) = mm;
+        *(reinterpret_cast<float4*>(x.v + row) + c4) = vv;
+      }
+    }
     __syncthreads();                                    // the next call's warp 0 overwrites misc->skip
     return sk;
   };
@@ -561,11 +616,12 @@ k_step_fused(StepParams a, FusedExtra x, VmbLayout L, const unsigned char* image
     {
     // ===================== compute threads of point group g ============================================================
     const float isc = 1.0f / a.scale[b];
-    float inv_nd = 0.f, inv_no = 0.f, inv_ns = 0.f;
-    if (!a.fwd_only) {
-      inv_nd = 1.f / ((float)cnt[b * 3 + 0] + 1e-10f);
-      inv_no = 1.f / ((float)cnt[b * 3 + 1] + 1e-10f);
-      inv_ns = 1.f / ((float)cnt[b * 3 + 2] + 1e-10f);
+    bool seg_w = false;               // w_d / w_c / w_o hold this segment's object?
+    if (!a.fwd_only && !pub_counts) {
+      w_d = on_d / ((float)cnt[b * 3 + 0] + 1e-10f);
+      w_c = on_c / ((float)cnt[b * 3 + 1] + 1e-10f);
+      w_o = on_o / ((float)cnt[b * 3 + 2] + 1e-10f);
+      seg_w = true;
     }
 
     // operands written -> fence for the async proxy -> group barrier -> the elected lane of the group's first warp issues
@@ -637,23 +693,35 @@ k_step_fused(StepParams a, FusedExtra x, VmbLayout L, const unsigned char* image
 
     // prefetched inputs of the next tile (global-load latency overlaps the current tile)
     float nx = 0.f, ny = 0.f, nz = 0.f, nzv = 0.f, n_gd = 0.f, n_c0 = 0.f, n_c1 = 0.f, n_c2 = 0.f;
-    int n_sm = 0;
+    // (nothing computes on the loaded values here: the first use of a load stalls the warp for the memory latency)
+    int n_sem = 0, n_msk = 0;
+    bool n_live = false;
+    // this object's base pointers, formed once per segment (the kernel-parameter loads and 64-bit stride products
+    // otherwise sit, with their latencies, in every tile's prefetch)
+    const float* pcs_b = a.pcs + (size_t)b * a.pcs_stride + (size_t)sidx * 3;
+    const float* z_b = a.z + (size_t)b * a.z_stride + sidx;
+    const float* gd_b = a.gt_depth + (size_t)b * a.gt_depth_stride;
+    const float* gc_b = a.gt_colour + (size_t)b * a.gt_colour_stride;
+    const unsigned char* sem_b = a.sem + (size_t)b * a.sem_stride;
+    const unsigned char* msk_b = a.mask + (size_t)b * a.mask_stride;
+    const bool want_targets = hsel == 0 && !a.fwd_only;
     auto prefetch = [&](int t) {
-      nx = ny = nz = nzv = 0.f; n_gd = n_c0 = n_c1 = n_c2 = 0.f; n_sm = 0;
+      nx = ny = nz = nzv = 0.f; n_gd = n_c0 = n_c1 = n_c2 = 0.f; n_sem = 0; n_msk = 0; n_live = false;
       if (t >= t1 || !lane_used) return;
       const int ray = t * nr + ray_in_tile;
       if (ray >= R) return;
-      const size_t pi = (size_t)ray * S + sidx;
-      const float* pp = a.pcs + (size_t)b * a.pcs_stride + pi * 3;
+      const size_t pi = (size_t)ray * S;
+      const float* pp = pcs_b + pi * 3;
       nx = pp[0]; ny = pp[1]; nz = pp[2];
-      if (hsel == 0 && !a.fwd_only) {                   // the render / loss lanes: every lane of a ray reads the ray's targets
-        nzv = a.z[(size_t)b * a.z_stride + pi];
-        n_gd = a.gt_depth[(size_t)b * a.gt_depth_stride + ray];
-        const float* gcp = a.gt_colour + (size_t)b * a.gt_colour_stride + (size_t)ray * 3;
+      if (want_targets) {                               // the render / loss lanes: every lane of a ray reads the ray's targets
+        nzv = z_b[pi];
+        n_gd = gd_b[ray];
+        const float* gcp = gc_b + (size_t)ray * 3;
         n_c0 = gcp[0]; n_c1 = gcp[1]; n_c2 = gcp[2];
-        n_sm = (int)a.sem[(size_t)b * a.sem_stride + ray] | ((int)a.mask[(size_t)b * a.mask_stride + ray] << 8);
+        n_sem = sem_b[ray];
+        n_msk = msk_b[ray];
       }
-      n_sm |= 0x10000;                                   // live point
+      n_live = true;                                      // live point
     };
     prefetch(t_first);
 
@@ -666,7 +734,8 @@ k_step_fused(StepParams a, FusedExtra x, VmbLayout L, const unsigned char* image
       const float t0x = nx * isc, t1x = ny * isc, t2x = nz * isc, zv = nzv;
       const uint64_t tp0 = um::pk2(t0x, t0x), tp1 = um::pk2(t1x, t1x), tp2 = um::pk2(t2x, t2x);
       const float gd = n_gd, gc0 = n_c0, gc1 = n_c1, gc2 = n_c2;
-      const int smv = n_sm;
+      const int sv = n_sem, mv = n_msk;
+      const bool live = n_live;
       [[maybe_unused]] int tre = 16 * ((t - t_first) / t_step);
       TRE();
       prefetch(t + t_step);
@@ -675,12 +744,25 @@ k_step_fused(StepParams a, FusedExtra x, VmbLayout L, const unsigned char* image
         uint4* e1 = reinterpret_cast<uint4*>(act + FG_E1 * FGB + p * 16);
         uint4* e2 = reinterpret_cast<uint4*>(act + FG_E2 * FGB + p * 16);
         const int q0 = hsel ? 3 : 0, q1 = hsel ? 5 : 3;
+        // software pipeline over the 4-direction chunks: the NEXT chunk's projections, range reduction and MUFU
+        // sin / cos are issued before the CURRENT chunk's doubling recurrence, which hides their latency
+        uint64_t s01, s23, c01, c23;
+        {
+          uint64_t pj01, pj23;
+          um::project4(Bd, q0, tp0, tp1, tp2, pj01, pj23);
+          um::sincos4_x2(pj01, pj23, s01, s23, c01, c23);
+        }
 #pragma unroll 1
         for (int q = q0; q < q1; ++q) {                // directions 4q .. 4q+3
           float sv[4][6];
-          uint64_t pj01, pj23;
-          um::project4(Bd, q, tp0, tp1, tp2, pj01, pj23);
-          um::sin_ladder4_x2(pj01, pj23, sv);
+          uint64_t ns01 = 0, ns23 = 0, nc01 = 0, nc23 = 0;
+          if (q + 1 < q1) {
+            uint64_t pj01, pj23;
+            um::project4(Bd, q + 1, tp0, tp1, tp2, pj01, pj23);
+            um::sincos4_x2(pj01, pj23, ns01, ns23, nc01, nc23);
+          }
+          um::sin_doubling4_x2(s01, s23, c01, c23, sv);
+          s01 = ns01; s23 = ns23; c01 = nc01; c23 = nc23;
           TRE();
           if (q == q0 && wb_pending) {                  // the previous tile's deferred MMAs still read E1 / DPR / FC3
             um::mbar_wait_or_trap(&misc->wb[g], wph); wph ^= 1; wb_pending = false;
@@ -734,7 +816,6 @@ k_step_fused(StepParams a, FusedExtra x, VmbLayout L, const unsigned char* image
       STAGE_BEGIN(5);                                   // out_color runs while the alpha-only part of the render is computed
       // ---- heads + volume render + losses + ray gradients, all in registers of the hsel == 0 warps ---------------
       // rays never straddle a warp: the scans over the sample axis are warp shuffles
-      const bool live = (smv & 0x10000) != 0;
       auto raysum = [&](float v) {                      // per-ray sum: guarded tree reduction to the ray's first lane, broadcast
 #pragma unroll
         for (int off = 1; off < 32; off <<= 1) {
@@ -744,6 +825,21 @@ k_step_fused(StepParams a, FusedExtra x, VmbLayout L, const unsigned char* image
       };
       float araw = 0.f, occ = 0.f, fr = 1.f, Tr = 1.f, w = 0.f, D = 0.f, O = 0.f, V = 0.f;
       if (hsel == 0) {                                  // alpha's tile was complete with stage 4
+        if (!seg_w && pub_counts) {                     // cooperative launch: acquire the published mask counts (first render only)
+          if (!cnt_ready) {
+            const volatile unsigned int* pubd = gbar + 2;
+            unsigned int spins = 0;
+            while (*pubd < (unsigned int)a.B) { if (++spins > 2000000000u) __trap(); }
+            __threadfence();
+            cnt_ready = true;
+          }
+          const volatile unsigned int* ef = gbar + 3;
+          const volatile int* cp = x.counts_pub + b * 4;
+          w_d = (ef[0] ? 0.f : 1.f) / ((float)cp[0] + 1e-10f);
+          w_c = (ef[1] ? 0.f : 1.f) / ((float)cp[1] + 1e-10f);
+          w_o = (ef[2] ? 0.f : 1.f) / ((float)cp[2] + 1e-10f);
+          seg_w = true;
+        }
         float hv[8];
         um::tmem_ld8(tA + TC_ALPHA, hv);
         ptx::tmem_ld_wait();
@@ -782,7 +878,6 @@ k_step_fused(StepParams a, FusedExtra x, VmbLayout L, const unsigned char* image
           }
         } else {
           const float C0 = raysum(w * c0), C1 = raysum(w * c1), C2 = raysum(w * c2);
-          const int sv = smv & 0xff, mv = (smv >> 8) & 0xff;
           const float m_o = (live && sv != 0) ? 1.f : 0.f, m_s = (live && sv != 2) ? 1.f : 0.f, m_d = (mv != 0) ? m_o : 0.f;
           const float info = 1.f / (sqrtf(V) + 1e-4f);                            // render_rays.py:74-79
           const float e_d = D - gd, e_o = O - m_o, e_c0 = C0 - gc0, e_c1 = C1 - gc1, e_c2 = C2 - gc2;
@@ -791,15 +886,15 @@ k_step_fused(StepParams a, FusedExtra x, VmbLayout L, const unsigned char* image
             if (a.r_var) a.r_var[(size_t)b * R + ray] = V;
             if (a.r_opacity) a.r_opacity[(size_t)b * R + ray] = O;
             if (a.r_colour) { float* rc = a.r_colour + ((size_t)b * R + ray) * 3; rc[0] = C0; rc[1] = C1; rc[2] = C2; }
-            ls_d += on_d * fabsf(e_d) * m_d * info * inv_nd;
-            ls_c += on_c * (fabsf(e_c0) + fabsf(e_c1) + fabsf(e_c2)) * m_o * inv_no;
-            ls_o += on_o * fabsf(e_o) * m_s * inv_ns;
+            ls_d += w_d * fabsf(e_d) * m_d * info;
+            ls_c += w_c * (fabsf(e_c0) + fabsf(e_c1) + fabsf(e_c2)) * m_o;
+            ls_o += w_o * fabsf(e_o) * m_s;
           }
           if (a.backward) {
-            const float gD = LS * on_d * vmb_sign(e_d) * m_d * info * inv_nd;
-            const float kc = LS * on_c * a.cs * m_o * inv_no;
+            const float gD = LS * w_d * vmb_sign(e_d) * m_d * info;
+            const float kc = LS * w_c * a.cs * m_o;
             const float gC0 = kc * vmb_sign(e_c0), gC1 = kc * vmb_sign(e_c1), gC2 = kc * vmb_sign(e_c2);
-            const float gO = LS * on_o * a.os * vmb_sign(e_o) * m_s * inv_ns;
+            const float gO = LS * w_o * a.os * vmb_sign(e_o) * m_s;
             // d(loss)/d(occ_s) through the termination product: G_s T_s - (sum_{k>s} G_k w_k) / (1 - occ_s + 1e-10)
             const float Gs = fmaf(gD, zv, fmaf(gC0, c0, fmaf(gC1, c1, fmaf(gC2, c2, gO))));
             float suf = Gs * w;                                                   // inclusive suffix scan
@@ -838,6 +933,12 @@ k_step_fused(StepParams a, FusedExtra x, VmbLayout L, const unsigned char* image
       // ---- PE backward: dproj_d = pi * sum_k 2^k g_{k,d} cos(pi 2^k proj_d), written as an fp16 block --------------
       {
         const int q0 = hsel ? 3 : 0, q1 = hsel ? 5 : 3;
+        uint64_t c01, c23;
+        {
+          uint64_t pj01, pj23;
+          um::project4(Bd, q0, tp0, tp1, tp2, pj01, pj23);
+          um::cos4_x2(pj01, pj23, c01, c23);
+        }
 #pragma unroll 1
         for (int q = q0; q < q1; ++q) {
           float g1a[8], g1b[8], g2[8];
@@ -845,9 +946,14 @@ k_step_fused(StepParams a, FusedExtra x, VmbLayout L, const unsigned char* image
           um::tmem_ld8(tE + 16 * q + 16, g1b);         //                          4q+2, 4q+3
           um::tmem_ld8(tA + 8 * q, g2);                // emb2 cols (k = 4, 5)
           float cv[4][6], dp[4];
-          uint64_t pj01, pj23;
-          um::project4(Bd, q, tp0, tp1, tp2, pj01, pj23);
-          um::cos_ladder4_x2(pj01, pj23, cv);
+          uint64_t nc01 = 0, nc23 = 0;
+          if (q + 1 < q1) {                            // next chunk's front half before this chunk's recurrence
+            uint64_t pj01, pj23;
+            um::project4(Bd, q + 1, tp0, tp1, tp2, pj01, pj23);
+            um::cos4_x2(pj01, pj23, nc01, nc23);
+          }
+          um::cos_doubling4_x2(c01, c23, cv);
+          c01 = nc01; c23 = nc23;
           ptx::tmem_ld_wait();
 #pragma unroll
           for (int dd = 0; dd < 4; ++dd) {
@@ -995,7 +1101,7 @@ k_step_fused(StepParams a, FusedExtra x, VmbLayout L, const unsigned char* image
     // ---- grid-wide finish: every CTA is resident (cooperative launch), all of them end their tiles within one round
     // of each other, and the reduction of ALL objects' partial rows + AdamW is split evenly over the grid (less than one
     // float4 of the parameter block per thread) instead of one object per SM on the kernel's tail.
-    unsigned int* gbar = x.obj_done + 2 * a.B;          // [0] arrive, [1] depart;  x.obj_done[B + b] = skip flag of object b
+    // gbar[0] arrive, gbar[1] depart;  x.obj_done[B + b] = skip flag of object b
     __threadfence();
     __syncthreads();
     if (tid == 0) {
@@ -1007,6 +1113,7 @@ k_step_fused(StepParams a, FusedExtra x, VmbLayout L, const unsigned char* image
     __threadfence();
     if (tid == 0) TRF(3, 205);
     const int n4 = L.stride >> 2;
+    if (tid == 0) TRF(3, 206);
     const long long W = (long long)a.B * n4;
     const long long lo = (W * blockIdx.x) / G, hi = (W * (blockIdx.x + 1)) / G;
     for (int b = (int)(lo / n4); (long long)b * n4 < hi; ++b) {
@@ -1015,8 +1122,10 @@ k_step_fused(StepParams a, FusedExtra x, VmbLayout L, const unsigned char* image
       const int skip = finish_rows(b, i_lo, i_hi, i_lo == 0);
       if (i_lo == 0 && tid == 0) x.obj_done[a.B + b] = (unsigned int)skip;
     }
+    if (tid == 0) TRF(3, 207);          // this CTA's slices reduced + updated
     __threadfence();
     __syncthreads();
+    if (tid == 0) TRF(3, 208);          // fenced
     if (tid == 0) misc->fin = (atomicAdd(&gbar[1], 1u) + 1u == (unsigned int)G) ? 1 : 0;
     __syncthreads();
     if (misc->fin) {                                    // the last CTA to leave: step numbers, re-arm the barrier
@@ -1024,7 +1133,7 @@ k_step_fused(StepParams a, FusedExtra x, VmbLayout L, const unsigned char* image
       if (x.fuse_adam && x.step_counter && a.backward)
         for (int b = tid; b < a.B; b += NT) if (x.obj_done[a.B + b] == 0u) x.step_counter[b] += 1;
       __syncthreads();
-      if (tid == 0) { gbar[0] = 0u; gbar[1] = 0u; }
+      if (tid == 0) { gbar[0] = 0u; gbar[1] = 0u; gbar[2] = 0u; gbar[3] = 0u; gbar[4] = 0u; gbar[5] = 0u; }
     }
   }
 

@@ -92,6 +92,7 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
 #define VMB_SPIN_LIMIT 50000000u
 #endif
 __device__ __forceinline__ void mbar_wait_or_trap(uint64_t* bar, uint32_t parity) {
+#pragma unroll 1
   for (uint32_t i = 0; i < VMB_SPIN_LIMIT; ++i)
     if (ptx::mbar_try_wait(bar, parity)) return;
   __trap();
@@ -153,19 +154,34 @@ __device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) { u
 __device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) { uint64_t d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
 __device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) { uint64_t d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
 
-// sin(pi 2^k x), k = 0..5, for four directions held as two packed pairs (d0,d1 | d2,d3): same recurrence as sin_ladder4
-__device__ __forceinline__ void sin_ladder4_x2(uint64_t pj01, uint64_t pj23, float (&s)[4][6]) {
-  float p[4];
+// Front half of the ladders: range reduction (sin/cos(pi x) have period 2) and the MUFU sin / cos of four directions
+// held as two packed pairs (d0,d1 | d2,d3).  Split from the doubling recurrence so that the caller can issue the next
+// four directions' front (shared-memory loads, FRND, MUFU: the long latencies) before the current four's recurrence.
+__device__ __forceinline__ void sincos4_x2(uint64_t pj01, uint64_t pj23, uint64_t& s01, uint64_t& s23, uint64_t& c01, uint64_t& c23) {
+  float p[4], s[4], c[4];
   upk2(pj01, p[0], p[1]); upk2(pj23, p[2], p[3]);
-  float c[4];
 #pragma unroll
   for (int d = 0; d < 4; ++d) {
-    const float r = p[d] - 2.0f * rintf(0.5f * p[d]);          // exact: sin(pi x) has period 2
-    s[d][0] = __sinf(VMB_PI_F * r);
+    const float r = p[d] - 2.0f * rintf(0.5f * p[d]);
+    s[d] = __sinf(VMB_PI_F * r);
     c[d] = __cosf(VMB_PI_F * r);
   }
-  uint64_t s01 = pk2(s[0][0], s[1][0]), s23 = pk2(s[2][0], s[3][0]), c01 = pk2(c[0], c[1]), c23 = pk2(c[2], c[3]);
+  s01 = pk2(s[0], s[1]); s23 = pk2(s[2], s[3]); c01 = pk2(c[0], c[1]); c23 = pk2(c[2], c[3]);
+}
+__device__ __forceinline__ void cos4_x2(uint64_t pj01, uint64_t pj23, uint64_t& c01, uint64_t& c23) {
+  float p[4], c[4];
+  upk2(pj01, p[0], p[1]); upk2(pj23, p[2], p[3]);
+#pragma unroll
+  for (int d = 0; d < 4; ++d) {
+    const float r = p[d] - 2.0f * rintf(0.5f * p[d]);
+    c[d] = __cosf(VMB_PI_F * r);
+  }
+  c01 = pk2(c[0], c[1]); c23 = pk2(c[2], c[3]);
+}
+// sin(pi 2^k x), k = 0..5: angle doubling on packed pairs (FADD2 / FMUL2 / FFMA2), same recurrence as sin_ladder4
+__device__ __forceinline__ void sin_doubling4_x2(uint64_t s01, uint64_t s23, uint64_t c01, uint64_t c23, float (&s)[4][6]) {
   const uint64_t one = pk2(1.0f, 1.0f), neg = pk2(-1.0f, -1.0f);
+  upk2(s01, s[0][0], s[1][0]); upk2(s23, s[2][0], s[3][0]);
 #pragma unroll
   for (int k = 1; k < 6; ++k) {
     const uint64_t d01 = add2(s01, s01), d23 = add2(s23, s23);
@@ -176,16 +192,9 @@ __device__ __forceinline__ void sin_ladder4_x2(uint64_t pj01, uint64_t pj23, flo
   }
 }
 // cos(pi 2^k x), k = 0..5, four directions as two packed pairs
-__device__ __forceinline__ void cos_ladder4_x2(uint64_t pj01, uint64_t pj23, float (&c)[4][6]) {
-  float p[4];
-  upk2(pj01, p[0], p[1]); upk2(pj23, p[2], p[3]);
-#pragma unroll
-  for (int d = 0; d < 4; ++d) {
-    const float r = p[d] - 2.0f * rintf(0.5f * p[d]);
-    c[d][0] = __cosf(VMB_PI_F * r);
-  }
-  uint64_t c01 = pk2(c[0][0], c[1][0]), c23 = pk2(c[2][0], c[3][0]);
+__device__ __forceinline__ void cos_doubling4_x2(uint64_t c01, uint64_t c23, float (&c)[4][6]) {
   const uint64_t neg = pk2(-1.0f, -1.0f);
+  upk2(c01, c[0][0], c[1][0]); upk2(c23, c[2][0], c[3][0]);
 #pragma unroll
   for (int k = 1; k < 6; ++k) {
     c01 = fma2(add2(c01, c01), c01, neg); c23 = fma2(add2(c23, c23), c23, neg);

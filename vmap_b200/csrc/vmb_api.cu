@@ -27,6 +27,8 @@ struct vmb_handle {
   unsigned int* d_smax;   // [max_obj] sampler: per-object max sampled depth (order-preserving key)
   float* d_partials;      // fused step: [(max_obj + n_sm)][stride] per-(CTA, object) gradient partials (allocated on first use)
   unsigned int* d_objdone;// fused step: [max_obj] finished-segment counters (self-resetting)
+  float2* d_bc;           // AdamW bias corrections per step number for (bc_b1, bc_b2), built on the host in double precision
+  double bc_b1, bc_b2;
   int img_halves;
   bool umma_ok;           // hidden 32: fused tcgen05 kernel + its pre-swizzled fp16 image
   bool lw_ok;             // hidden 64/128/256: layer-wise tcgen05 GEMM path + row-major fp16 image
@@ -120,7 +122,7 @@ int vmb_create(vmb_handle** out, int device, int max_obj, int hidden, int n_freq
   h->n_sm = 148;
   cudaDeviceGetAttribute(&h->n_sm, cudaDevAttrMultiProcessorCount, device);
   h->L = vmb_make_layout(hidden, n_freq);
-  h->d_counts = nullptr; h->d_img_index = nullptr; h->d_ticket = nullptr; h->d_smax = nullptr; h->d_partials = nullptr; h->d_objdone = nullptr; h->img_halves = 0; h->umma_ok = false; h->lw_ok = false;
+  h->d_counts = nullptr; h->d_img_index = nullptr; h->d_ticket = nullptr; h->d_smax = nullptr; h->d_partials = nullptr; h->d_objdone = nullptr; h->d_bc = nullptr; h->bc_b1 = h->bc_b2 = -1.0; h->img_halves = 0; h->umma_ok = false; h->lw_ok = false;
   cudaError_t e = cudaMalloc(&h->d_counts, sizeof(int) * 4 * max_obj);
   if (e == cudaSuccess) e = cudaMalloc(&h->d_ticket, sizeof(unsigned int));
   if (e == cudaSuccess) e = cudaMemset(h->d_ticket, 0, sizeof(unsigned int));
@@ -156,6 +158,7 @@ void vmb_destroy(vmb_handle* h) {
   if (h->d_smax) cudaFree(h->d_smax);
   if (h->d_partials) cudaFree(h->d_partials);
   if (h->d_objdone) cudaFree(h->d_objdone);
+  if (h->d_bc) cudaFree(h->d_bc);
   h->ws.release();
   h->ws_fwd.release();
   delete h;
@@ -211,6 +214,28 @@ static bool deterministic_mode() {
   return e && e[0] == '1';
 }
 
+// Device table of AdamW's bias corrections (1 - b1^t, sqrt(1 - b2^t)) for t < BC_N, computed in double precision like
+// torch.optim.adamw does; the kernels index it with the per-object device step number.  Rebuilt when the betas change
+// (never during stream capture: a captured graph would keep using the pointer, whose CONTENT is what changes).
+constexpr int BC_N = 20480;
+static int ensure_bc_table(vmb_handle* h, double b1, double b2, cudaStream_t st) {
+  if (h->d_bc && h->bc_b1 == b1 && h->bc_b2 == b2) return VMB_OK;
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  cudaStreamIsCapturing(st, &cs);
+  if (cs != cudaStreamCaptureStatusNone)
+    return fail(h, VMB_E_CUDA, "AdamW bias-correction table must be built outside stream capture (run one step eagerly first)");
+  if (!h->d_bc) CUDA_TRY(h, cudaMalloc(&h->d_bc, sizeof(float2) * BC_N));
+  std::vector<float2> tab(BC_N);
+  for (int t = 0; t < BC_N; ++t) {
+    const double tt = t < 1 ? 1.0 : (double)t;
+    tab[t] = make_float2((float)(1.0 - std::pow(b1, tt)), (float)std::sqrt(1.0 - std::pow(b2, tt)));
+  }
+  CUDA_TRY(h, cudaStreamSynchronize(st));          // earlier launches may still read the old content
+  CUDA_TRY(h, cudaMemcpy(h->d_bc, tab.data(), sizeof(float2) * BC_N, cudaMemcpyHostToDevice));
+  h->bc_b1 = b1; h->bc_b2 = b2;
+  return VMB_OK;
+}
+
 static int launch_adamw(vmb_handle* h, int n_obj, float* params, float* grads, float* m, float* v, void* image,
                         const float* loss_terms, int* status, const AdamScalars& q, float eps, int zero_grads,
                         int* step_counter, cudaStream_t st) {
@@ -224,6 +249,11 @@ static int launch_adamw(vmb_handle* h, int n_obj, float* params, float* grads, f
   p.lr_wd = q.lr_wd; p.one_m_b1 = q.one_m_b1; p.b2 = q.b2; p.one_m_b2 = q.one_m_b2;
   p.step_counter = step_counter; p.ticket = h->d_ticket; p.lr = q.lr; p.b1 = q.b1; p.b2d = q.b2d;
   p.log_b1 = (float)std::log(q.b1); p.log_b2 = (float)std::log(q.b2d);
+  if (step_counter) {
+    const int rcb = ensure_bc_table(h, q.b1, q.b2d, st);
+    if (rcb != VMB_OK) return rcb;
+    p.bc_table = h->d_bc; p.bc_n = BC_N;
+  }
   p.step_size = q.step_size; p.bc2_sqrt = q.bc2_sqrt;
   p.eps = eps;
   p.zero_grads = zero_grads;
@@ -275,7 +305,7 @@ int vmb_step(vmb_handle* h, const vmb_step_args* a, void* stream) {
     if (rc0 != VMB_OK) return rc0;
     FusedExtra fx;
     memset(&fx, 0, sizeof(fx));
-    fx.partials = h->d_partials; fx.obj_done = h->d_objdone; fx.counts_in = a->counts;
+    fx.partials = h->d_partials; fx.obj_done = h->d_objdone; fx.counts_in = a->counts; fx.counts_pub = h->d_counts;
     fx.fuse_adam = a->fuse_adam ? 1 : 0;
     fx.single_group = deterministic_mode() ? 1 : 0;
     if (a->fuse_adam) {
@@ -284,6 +314,11 @@ int vmb_step(vmb_handle* h, const vmb_step_args* a, void* stream) {
       fx.step_counter = a->step_counter; fx.step_size = q.step_size; fx.bc2_sqrt = q.bc2_sqrt;
       fx.lr = q.lr; fx.b1d = q.b1; fx.b2d = q.b2d;
       fx.log_b1 = (float)std::log(q.b1); fx.log_b2 = (float)std::log(q.b2d);
+      if (a->step_counter) {
+        const int rcb = ensure_bc_table(h, q.b1, q.b2d, st);
+        if (rcb != VMB_OK) return rcb;
+        fx.bc_table = h->d_bc; fx.bc_n = BC_N;
+      }
       fx.lr_wd = q.lr_wd; fx.one_m_b1 = q.one_m_b1; fx.b2 = q.b2; fx.one_m_b2 = q.one_m_b2; fx.eps = a->eps;
       fx.guard_loss = a->guard_loss; fx.status = a->status;
     }
