@@ -40,6 +40,11 @@ MMA_CYCLES = {16: 36.0, 32: 40.0, 48: 44.0, 96: 56.0}
 MMA_MIX = {32: 73, 16: 20, 96: 4, 48: 2}
 
 
+def log(msg):
+    """Progress on stderr (stdout carries exactly one JSON line)."""
+    print(f"[bench rank {os.environ.get('RANK', '0')}] {msg}", file=sys.stderr, flush=True)
+
+
 def workload_name(world):
     """The SAME string in both arms (the driver compares configs)."""
     return f"vMAP {N_OBJ} objects per GPU x {N_RAYS} rays x {N_SAMPLES} samples, hidden {HIDDEN} (BASELINE cfg 2 per GPU)"
@@ -377,6 +382,7 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     impl = os.environ.get("VMB_IMPL", "auto")
     fused = impl in ("auto", "umma")
+    log(f"world {world}, device {dev}, impl {impl}")
 
     sampler = ClockSampler(local)                 # runs for the whole process; windowed to the timed arms below
     if rank == 0:
@@ -413,6 +419,7 @@ def run_ours(args):
         return ms
 
     K, W = args.steps, max(args.warmup, 3)
+    log(f"input pool of {n_pool} batches ready")
     for i in range(3):                               # eager warm-up (sets kernel attributes, allocates scratch)
         ens.step(dev_pool[i % n_pool].views)
     if use_graphs:                                   # one captured step per input buffer
@@ -439,6 +446,7 @@ def run_ours(args):
     t_wall1 = time.time()
     ms_total = max_over_ranks(e0.elapsed_time(e1))
     ens.check_status()
+    log(f"device-resident arm: {ms_total / K * 1e3:.1f} us/step")
 
     # ---- same steps launched eagerly with CUDA events around the step kernel (roofline) ----
     k1_events = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
@@ -484,6 +492,7 @@ def run_ours(args):
     clocks = sampler.stop(t_wall0, time.time()) if rank == 0 else None
 
     # ---- extra arms -------------------------------------------------------------------------------------------------
+    log(f"end-to-end arm: {e2e_ms / K * 1e3:.1f} us/step")
     extras = {}
     if not args.no_extras:
         try:

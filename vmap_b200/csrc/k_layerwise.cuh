@@ -52,7 +52,29 @@ struct Workspace {
   void release() {
     void* ptrs[] = {E, X1, X2, X3, X4, XC, dYa, dYb, dYc, dh16, occ, col, dhead, dalpha_s, dE};
     for (void* q : ptrs) if (q) cudaFree(q);
+    cudaStream_t keep_s = side; cudaEvent_t km[5], ks[2];
+    for (int i = 0; i < 5; ++i) km[i] = ev_main[i];
+    for (int i = 0; i < 2; ++i) ks[i] = ev_side[i];
     *this = Workspace();
+    side = keep_s;
+    for (int i = 0; i < 5; ++i) ev_main[i] = km[i];
+    for (int i = 0; i < 2; ++i) ev_side[i] = ks[i];
+  }
+  // side stream of the backward pass: the weight-gradient GEMMs of a layer depend only on that layer's dY, so they run
+  // beside the input-gradient chain (fork / join with events; inside a stream capture they become parallel graph branches)
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_main[5] = {}, ev_side[2] = {};
+  cudaError_t ensure_streams() {
+    if (side) return cudaSuccess;
+    cudaError_t e = cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking);
+    for (auto& v : ev_main) if (e == cudaSuccess) e = cudaEventCreateWithFlags(&v, cudaEventDisableTiming);
+    for (auto& v : ev_side) if (e == cudaSuccess) e = cudaEventCreateWithFlags(&v, cudaEventDisableTiming);
+    return e;
+  }
+  void destroy_streams() {
+    for (auto& v : ev_main) if (v) { cudaEventDestroy(v); v = nullptr; }
+    for (auto& v : ev_side) if (v) { cudaEventDestroy(v); v = nullptr; }
+    if (side) { cudaStreamDestroy(side); side = nullptr; }
   }
   bool in_graph = false;       // a captured CUDA graph holds these pointers: the buffers must never move again
   // Grow-only.  Never reallocates while the stream is capturing or after a capture has baked the pointers
@@ -431,11 +453,14 @@ static int step_object(Workspace& ws, const VmbLayout& L, const StepParams& sp, 
   k_lw_heads_bwd<H><<<nblk, 128, 0, st>>>(ws.XC, ws.dhead, Pb, L, np, ws.dYc, ws.dh16, ws.dalpha_s, G);
   const int ksplit = 4096, zs = (int)((np + ksplit - 1) / ksplit);
   // weight gradient: G[o*ldm + n] += sum_p dY[p][o] * X[p][n]   (A = dY^T, B = X, both MN-major, split over points)
+  LW_TRY(ws.ensure_streams());
+  cudaStream_t sd = ws.side;
+  auto fork = [&](int i) { cudaEventRecord(ws.ev_main[i], st); return cudaStreamWaitEvent(sd, ws.ev_main[i], 0); };
   auto wgrad = [&](const __half* dY, const Operand& xb, int N, int goff, int ldm, int n_valid, int ones_col, int boff) {
     GemmArgs g; memset(&g, 0, sizeof(g));
     g.M = H; g.N = N; g.K1 = (int)np; g.K2 = 0; g.ksplit = ksplit; g.gdst = G + goff; g.ldgd = ldm; g.ldgn = 1; g.n_lo = 0;
     g.n_valid = n_valid; g.ones_col = ones_col; g.gbias = boff >= 0 ? G + boff : nullptr; g.scale = INV_LS;
-    return launch_gemm<1, 1, EPI_ATOMIC>(Operand{dY, np, H, H}, none, xb, g, (H + BM - 1) / BM, (N + BN - 1) / BN, zs, st);
+    return launch_gemm<1, 1, EPI_ATOMIC>(Operand{dY, np, H, H}, none, xb, g, (H + BM - 1) / BM, (N + BN - 1) / BN, zs, sd);
   };
   // input gradient through a weight block: out = gate(x_prev) * (dY @ W[:, c0:c0+N] (+ rank-1))   or fp32 into dE
   auto dgrad_gate = [&](const __half* dY, long long woff, int ldw, const __half* xprev, __half* out, const float* r1row, const float* r1col) {
@@ -454,9 +479,10 @@ static int step_object(Workspace& ws, const VmbLayout& L, const StepParams& sp, 
     GemmArgs g; memset(&g, 0, sizeof(g));
     g.M = H; g.N = 8; g.K1 = (int)np; g.ksplit = ksplit; g.ldgd = 1; g.scale = INV_LS; g.ones_col = -1;
     g.gdst = G + L.o_Wa; g.ldgn = 0; g.n_lo = 0; g.n_valid = 1;
-    LW_TRY((launch_gemm<1, 1, EPI_ATOMIC>(Operand{ws.X4, np, H, H}, none, Operand{ws.dh16, np, 8, 8}, g, (H + BM - 1) / BM, 1, zs, st)));
+    LW_TRY(fork(0));                                    // dYc (= d colour hidden), dh16 ready: heads + color_linear wgrads on the side stream
+    LW_TRY((launch_gemm<1, 1, EPI_ATOMIC>(Operand{ws.X4, np, H, H}, none, Operand{ws.dh16, np, 8, 8}, g, (H + BM - 1) / BM, 1, zs, sd)));
     g.gdst = G + L.o_Woc - H; g.ldgn = H; g.n_lo = 1; g.n_valid = 4;
-    LW_TRY((launch_gemm<1, 1, EPI_ATOMIC>(Operand{ws.XC, np, H, H}, none, Operand{ws.dh16, np, 8, 8}, g, (H + BM - 1) / BM, 1, zs, st)));
+    LW_TRY((launch_gemm<1, 1, EPI_ATOMIC>(Operand{ws.XC, np, H, H}, none, Operand{ws.dh16, np, 8, 8}, g, (H + BM - 1) / BM, 1, zs, sd)));
   }
   // color_linear
   LW_TRY(wgrad(ws.dYc, opX(ws.X4), H, L.o_Wcl, H + L.e2, H, -1, -1));
@@ -464,19 +490,26 @@ static int step_object(Workspace& ws, const VmbLayout& L, const StepParams& sp, 
   LW_TRY(dgrad_emb(ws.dYc, off_cl(H) + H, H + 48, E2W, E1W, 0));
   LW_TRY(dgrad_gate(ws.dYc, off_cl(H), H + 48, ws.X4, ws.dYa, ws.dalpha_s, Pb + L.o_Wa));          // dY4 -> dYa
   // mid2
+  LW_TRY(fork(1));
   LW_TRY(wgrad(ws.dYa, opX(ws.X3), H, L.o_Wm2, H, H, -1, -1));
-  k_lw_colsum<<<(int)((np + 511) / 512), 256, 0, st>>>(ws.dYa, np, H, G + L.o_bm2);
+  k_lw_colsum<<<(int)((np + 511) / 512), 256, 0, sd>>>(ws.dYa, np, H, G + L.o_bm2);
+  LW_TRY(cudaEventRecord(ws.ev_side[0], sd));           // the side stream is done reading dYc (dY of color_linear) and dYa (dY4)
   LW_TRY(dgrad_gate(ws.dYa, off_m2(H), H, ws.X3, ws.dYb, nullptr, nullptr));                        // dY3 -> dYb
   // cat_layer
+  LW_TRY(fork(2));
   LW_TRY(wgrad(ws.dYb, opX(ws.X2), H, L.o_Wcat, H + VMB_E1, H, -1, -1));
   LW_TRY(wgrad(ws.dYb, opE1, E1W, L.o_Wcat + H, H + VMB_E1, VMB_E1, ONES1, L.o_bcat));
+  LW_TRY(cudaStreamWaitEvent(st, ws.ev_side[0], 0));    // dYa / dYc are about to be overwritten
   LW_TRY(dgrad_gate(ws.dYb, off_cat(H), H + 96, ws.X2, ws.dYa, nullptr, nullptr));                  // dY2 -> dYa (dY3 stays in dYb)
   // mid1
+  LW_TRY(fork(3));
   LW_TRY(wgrad(ws.dYa, opX(ws.X1), H, L.o_Wm1, H, H, -1, -1));
-  k_lw_colsum<<<(int)((np + 511) / 512), 256, 0, st>>>(ws.dYa, np, H, G + L.o_bm1);
+  k_lw_colsum<<<(int)((np + 511) / 512), 256, 0, sd>>>(ws.dYa, np, H, G + L.o_bm1);
   LW_TRY(dgrad_gate(ws.dYa, off_m1(H), H, ws.X1, ws.dYc, nullptr, nullptr));                        // dY1 -> dYc (free since color_linear)
   // in_layer
+  LW_TRY(fork(4));
   LW_TRY(wgrad(ws.dYc, opE1, E1W, L.o_Win, VMB_E1, VMB_E1, ONES1, L.o_bin));
+  LW_TRY(cudaEventRecord(ws.ev_side[1], sd));
   // d emb1 = dY3 @ W_cat[:, H:] + dY1 @ W_in in ONE launch: A = [dY3 | dY1] along K, B = the two weight blocks
   {
     GemmArgs g; memset(&g, 0, sizeof(g));
@@ -498,6 +531,7 @@ static int step_object(Workspace& ws, const VmbLayout& L, const StepParams& sp, 
     }
   }
   k_lw_pe_bwd<<<nblk, 128, PEB_SMEM, st>>>(pcs, dirs, scale_p, np, ws.dE, G + L.o_B);
+  LW_TRY(cudaStreamWaitEvent(st, ws.ev_side[1], 0));    // join: every weight-gradient GEMM of this object has been enqueued before what follows
   LW_TRY(cudaGetLastError());
   return 0;
 }

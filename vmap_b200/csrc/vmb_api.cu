@@ -159,8 +159,8 @@ void vmb_destroy(vmb_handle* h) {
   if (h->d_partials) cudaFree(h->d_partials);
   if (h->d_objdone) cudaFree(h->d_objdone);
   if (h->d_bc) cudaFree(h->d_bc);
-  h->ws.release();
-  h->ws_fwd.release();
+  h->ws.release(); h->ws.destroy_streams();
+  h->ws_fwd.release(); h->ws_fwd.destroy_streams();
   delete h;
 }
 
