@@ -120,6 +120,9 @@ typedef struct vmb_step_args {
   float  lr, beta1, beta2, eps, weight_decay;
   int    guard_loss;                /* 1 = skip an object's update and raise the status bits if its loss explodes */
   int*   status;                    /* optional device int[4], bits OR-ed in                */
+  float* loss_sum;                  /* optional device float: receives the step's scalar loss, sum over objects of the
+                                       weighted totals (`loss.sum()` of loss.py:59-62), so the caller needs no reduction
+                                       launch of its own                                     */
 } vmb_step_args;
 
 int vmb_step(vmb_handle* h, const vmb_step_args* a, void* stream);

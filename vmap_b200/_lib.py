@@ -40,7 +40,7 @@ class StepArgs(C.Structure):
         ("k1_start_event", _vp), ("k1_stop_event", _vp),
         ("exp_avg", _vp), ("exp_avg_sq", _vp), ("step_counter", _vp), ("step", C.c_int),
         ("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float),
-        ("weight_decay", C.c_float), ("guard_loss", C.c_int), ("status", _vp),
+        ("weight_decay", C.c_float), ("guard_loss", C.c_int), ("status", _vp), ("loss_sum", _vp),
     ]
 
 

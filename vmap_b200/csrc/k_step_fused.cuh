@@ -70,6 +70,7 @@ struct FusedExtra {
   int* status;
   int single_group;           // 1: only point group 0 walks tiles -> one in-order wgrad MMA stream per SM -> bitwise reproducible
   int cooperative;            // 1: cooperative launch (all CTAs resident): an object's CTAs share its reduction + update
+  float* loss_sum;            // optional: sum over objects of the weighted loss totals, written by the last CTA to leave
 };
 
 namespace uf {
@@ -1132,6 +1133,12 @@ k_step_fused(StepParams a, FusedExtra x, VmbLayout L, const unsigned char* image
       __threadfence();
       if (x.fuse_adam && x.step_counter && a.backward)
         for (int b = tid; b < a.B; b += NT) if (x.obj_done[a.B + b] == 0u) x.step_counter[b] += 1;
+      if (x.loss_sum && warp == 0) {                    // scalar loss of the step (loss.py:59-62), fixed summation order
+        float s = 0.f;
+        for (int b = lane; b < a.B; b += 32) s += __ldcg(a.loss_terms + b * 4 + 3);
+        s = warp_sum(s);
+        if (lane == 0) *x.loss_sum = s;
+      }
       __syncthreads();
       if (tid == 0) { gbar[0] = 0u; gbar[1] = 0u; gbar[2] = 0u; gbar[3] = 0u; gbar[4] = 0u; gbar[5] = 0u; }
     }
@@ -1175,7 +1182,7 @@ static void fused_partition(int B, int npo, int G, uf::Ranges& rg) {
 }
 
 static int fused_launch_step(const VmbLayout& L, const StepParams& sp, const FusedExtra& fx, const void* image, int n_sm,
-                             cudaStream_t st, std::string& err) {
+                             cudaStream_t st, std::string& err, bool* cooperative = nullptr) {
   using namespace uf;
   if (L.H != 32 || L.nfreq != 6) { err = "fused step kernel: hidden must be 32 and n_freq 6"; return -4; }
   if (sp.S < 1 || sp.S > 32) { err = "fused step kernel: n_samples must be in [1, 32]"; return -4; }
@@ -1214,6 +1221,7 @@ static int fused_launch_step(const VmbLayout& L, const StepParams& sp, const Fus
     coop_ok[dev & 63] = v ? 1 : -1;
   }
   fxl.cooperative = (coop_ok[dev & 63] == 1 && !sp.fwd_only && getenv("VMB_NO_COOP") == nullptr) ? 1 : 0;
+  if (cooperative) *cooperative = fxl.cooperative != 0;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(NT); cfg.dynamicSmemBytes = smem_bytes; cfg.stream = st;

@@ -236,6 +236,14 @@ static int ensure_bc_table(vmb_handle* h, double b1, double b2, cudaStream_t st)
   return VMB_OK;
 }
 
+// scalar loss of a step for the paths that do not produce it inside their own kernels
+__global__ void k_loss_sum(const float* __restrict__ loss_terms, int B, float* __restrict__ out) {
+  float s = 0.f;
+  for (int b = threadIdx.x; b < B; b += 32) s += loss_terms[b * 4 + 3];
+  s = warp_sum(s);
+  if (threadIdx.x == 0) *out = s;
+}
+
 static int launch_adamw(vmb_handle* h, int n_obj, float* params, float* grads, float* m, float* v, void* image,
                         const float* loss_terms, int* status, const AdamScalars& q, float eps, int zero_grads,
                         int* step_counter, cudaStream_t st) {
@@ -325,8 +333,11 @@ int vmb_step(vmb_handle* h, const vmb_step_args* a, void* stream) {
     EvGuard evg{(cudaEvent_t)a->k1_stop_event, st};
     if (a->k1_start_event) cudaEventRecord((cudaEvent_t)a->k1_start_event, st);
     std::string err;
-    const int rc = fused_launch_step(h->L, sp, fx, a->image, h->n_sm, st, err);
+    fx.loss_sum = a->loss_sum;
+    bool coop = false;
+    const int rc = fused_launch_step(h->L, sp, fx, a->image, h->n_sm, st, err, &coop);
     if (rc != VMB_OK) return fail(h, rc, err);
+    if (a->loss_sum && !coop) { k_loss_sum<<<1, 32, 0, st>>>(a->loss_terms, a->n_obj, a->loss_sum); CUDA_TRY(h, cudaGetLastError()); }
     return VMB_OK;
   }
 
@@ -358,6 +369,7 @@ int vmb_step(vmb_handle* h, const vmb_step_args* a, void* stream) {
       return fail(h, VMB_E_ARG, "vmb_step: unknown impl");
     }
   }
+  if (a->loss_sum) { k_loss_sum<<<1, 32, 0, st>>>(a->loss_terms, a->n_obj, a->loss_sum); CUDA_TRY(h, cudaGetLastError()); }
   if (a->fuse_adam)
     return launch_adamw(h, a->n_obj, const_cast<float*>(a->params), a->grads, a->exp_avg, a->exp_avg_sq,
                         (h->umma_ok || h->lw_ok) ? const_cast<void*>(a->image) : nullptr,

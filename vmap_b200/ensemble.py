@@ -67,6 +67,7 @@ class VmapEnsemble:
         self.scale = (sc.expand(n_obj) if sc.dim() == 0 else sc).to(dev).contiguous().clone()
         self.loss_terms = torch.zeros(n_obj, 4, **f32)
         self.status = torch.zeros(4, dtype=torch.int32, device=dev)
+        self.loss_sum = torch.zeros(1, **f32)              # the step's scalar loss (sum over objects), written by vmb_step
         self.step_count = 0
         # per-object step numbers on the device: graph replay needs them there, and objects that join a stack later
         # (update_vmap(..., keep_optimizer_state=True)) keep their own bias correction
@@ -118,7 +119,7 @@ class VmapEnsemble:
 
     # ---- kernels ----------------------------------------------------------------------------
     def _step_args(self, batch, backward: bool, outputs=None, impl: Optional[str] = None, counts=None,
-                   fuse_adam: bool = False, guard_loss: bool = True):
+                   fuse_adam: bool = False, guard_loss: bool = True, loss_out: Optional[torch.Tensor] = None):
         pcs, z = batch["pcs"], batch["z"]
         B, R, S = pcs.shape[0], pcs.shape[1], pcs.shape[2]
         assert B == self.n_obj and pcs.shape[3] == 3 and tuple(z.shape) == (B, R, S)
@@ -146,6 +147,9 @@ class VmapEnsemble:
         a.counts = _ptr(counts)
         a.colour_scaling, a.opacity_scaling = self.colour_scaling, self.opacity_scaling
         a.backward = 1 if backward else 0
+        if loss_out is not None:
+            assert loss_out.dtype == torch.float32 and loss_out.device == self.device and loss_out.numel() >= 1
+            a.loss_sum = _ptr(loss_out)
         if fuse_adam:
             a.fuse_adam = 1
             a.exp_avg, a.exp_avg_sq = _ptr(self.exp_avg), _ptr(self.exp_avg_sq)
@@ -157,11 +161,11 @@ class VmapEnsemble:
 
     def forward_backward(self, batch, outputs=None, backward: bool = True, impl: Optional[str] = None,
                          counts: Optional[torch.Tensor] = None, k1_events=None, fuse_adam: bool = False,
-                         guard_loss: bool = True):
+                         guard_loss: bool = True, loss_out: Optional[torch.Tensor] = None):
         """K0 + K1: accumulates into ``self.grads`` and overwrites ``self.loss_terms``; with ``fuse_adam`` the
         optimiser update happens in the same call (``self.grads`` untouched at hidden 32).
         ``k1_events`` = (start, stop) torch.cuda.Event pair recorded around the K1 launch."""
-        a = self._step_args(batch, backward, outputs, impl, counts, fuse_adam, guard_loss)
+        a = self._step_args(batch, backward, outputs, impl, counts, fuse_adam, guard_loss, loss_out)
         if k1_events is not None:
             for ev in k1_events:
                 if not ev.cuda_event:
@@ -199,11 +203,14 @@ class VmapEnsemble:
         with torch.cuda.device(self.device):
             _lib.check(self._handle, self.lib.vmb_adam(self._handle, C.byref(a), _stream()), "vmb_adam")
 
-    def step(self, batch, impl: Optional[str] = None) -> torch.Tensor:
-        """One optimisation step (train.py:293-326) in one library call. Returns the summed loss (device scalar)."""
-        self.forward_backward(batch, impl=impl, fuse_adam=True)
+    def step(self, batch, impl: Optional[str] = None, loss_out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """One optimisation step (train.py:293-326) in one library call.  Returns the summed loss as a device scalar:
+        a view of ``loss_out`` (a float32 device tensor the call writes into) or of ``self.loss_sum``.  No reduction
+        launch on the Python side: the step kernel's last CTA writes it."""
+        out = self.loss_sum if loss_out is None else loss_out
+        self.forward_backward(batch, impl=impl, fuse_adam=True, loss_out=out)
         self.step_count += 1
-        return self.loss_terms[:, 3].sum()
+        return out.view(-1)[0]
 
     def capture_step(self, batch, impl: Optional[str] = None) -> "torch.cuda.CUDAGraph":
         """Capture the step (one launch at hidden 32) on ``batch``'s (fixed) buffers into a CUDA graph; refill the buffers

@@ -89,7 +89,7 @@ class FrameLoop:
                      tables=self.tables, out=self.out, offset_dev=self.counter)
         self.counter += 1
         for it in range(self.n_iter):
-            self.losses[it] = self.ens.step({k: v[:, it * R:(it + 1) * R] for k, v in self.out.items()})
+            self.ens.step({k: v[:, it * R:(it + 1) * R] for k, v in self.out.items()}, loss_out=self.losses[it:it + 1])
             if bg is not None:  # train.py:308-316
                 self.losses[it] += bg.ens.step({k: v[:, it * Rb:(it + 1) * Rb] for k, v in bg.out.items()})
 
