@@ -157,3 +157,23 @@ def test_step_is_reproducible(monkeypatch):
         e.forward_backward(batches[0])
         g.append(e.grads.clone())
     assert rel_l2(g[0], g[1]) < 1e-5
+
+
+@pytest.mark.parametrize("impl", ["umma", "fp32"])
+def test_step_returns_scalar_loss_without_a_reduction_launch(impl):
+    """``vmb_step_args.loss_sum``: the step writes sum_b loss_terms[b][3] (loss.py:59-62 followed by train.py's
+    ``batch_loss`` scalar) itself -- last CTA of the fused kernel, or a one-warp kernel behind the other paths."""
+    B, R, S = 5, 130, 10
+    params = vo.init_params(B, 32, seed=9)
+    ens = make_ensemble(params, 2.0, 32, impl=impl)
+    got, want = [], []
+    for it in range(3):
+        got.append(ens.step(to_dev(vo.synthetic_batch(B, R, S, seed=80 + it))))
+        want.append(ens.loss_terms[:, 3].double().sum().item())
+    ens.check_status()
+    assert len({g.data_ptr() for g in got}) == 3                  # ring slots: earlier results are not overwritten
+    for g, w in zip(got, want):
+        assert abs(float(g) - w) <= 1e-5 * abs(w)
+    out = torch.zeros(3, device=ens.device)
+    ens.step(to_dev(vo.synthetic_batch(B, R, S, seed=90)), loss_out=out[1:2])
+    assert out[0] == 0 and out[2] == 0 and abs(float(out[1]) - ens.loss_terms[:, 3].sum().item()) <= 1e-4 * float(out[1])

@@ -14,6 +14,7 @@ struct AdamParams {
   float* p; float* g; float* m; float* v;
   __half* image; const int* img_index; int img_halves;   // per-object image size in halves
   const float* loss_terms; int* status;
+  const float* loss_sum_src; float* loss_sum;   // optional: block 0 writes sum_b loss_sum_src[b][3] (the step's scalar loss)
   float lr_wd;                // 1 - lr*wd
   float one_m_b1, b2, one_m_b2;
   float step_size;            // lr / (1 - b1^t)
@@ -60,6 +61,12 @@ __global__ void __launch_bounds__(256) k_adamw(AdamParams a) {
     } else {
       s_step_size[threadIdx.x] = a.step_size; s_bc2_sqrt[threadIdx.x] = a.bc2_sqrt;
     }
+  }
+  if (a.loss_sum && blockIdx.x == 0 && threadIdx.x >= 32 && threadIdx.x < 64) {
+    float s = 0.f;
+    for (int b = threadIdx.x - 32; b < a.B; b += 32) s += a.loss_sum_src[b * 4 + 3];
+    s = warp_sum(s);
+    if (threadIdx.x == 32) *a.loss_sum = s;
   }
   __syncthreads();
   if (a.loss_terms) {       // render_rays.py:88-90: the reference aborts before the update

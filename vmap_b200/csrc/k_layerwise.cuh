@@ -191,6 +191,8 @@ struct RenderArgs {
   const int* counts; float cs, os; int backward;
   float* loss_terms; float* r_depth; float* r_var; float* r_colour; float* r_opacity;
 };
+// One warp per ray, lane = sample (n_samples <= 32): coalesced loads, transmittance as a warp product scan, the
+// backward's suffix sum as a warp scan -- a ray's 32 samples cost a handful of shuffles instead of five serial passes.
 __global__ void __launch_bounds__(128) k_lw_render(RenderArgs a, const float* __restrict__ occ, const float* __restrict__ col,
                                                    float* __restrict__ dhead) {
   __shared__ int s_on[3];
@@ -201,65 +203,64 @@ __global__ void __launch_bounds__(128) k_lw_render(RenderArgs a, const float* __
     s_on[threadIdx.x] = on; s_loss[threadIdx.x] = 0.f;
   }
   __syncthreads();
-  const int ray = blockIdx.x * 128 + threadIdx.x, S = a.S, b = a.b;
-  float l_d = 0.f, l_c = 0.f, l_o = 0.f;
-  if (ray < a.R) {
-    const long long pb = (long long)ray * S;
-    float T = 1.f, D = 0.f, O = 0.f, C0 = 0.f, C1 = 0.f, C2 = 0.f;
-    for (int s = 0; s < S; ++s) {
-      const float oc = occ[pb + s], w = oc * T;
-      D = fmaf(w, a.z[pb + s], D); O += w;
-      C0 = fmaf(w, col[(pb + s) * 3], C0); C1 = fmaf(w, col[(pb + s) * 3 + 1], C1); C2 = fmaf(w, col[(pb + s) * 3 + 2], C2);
-      T *= (1.f - oc + 1e-10f);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, S = a.S, b = a.b;
+  const unsigned FULL = 0xffffffffu;
+  const float inv_nd = 1.f / ((float)a.counts[b * 4 + 0] + 1e-10f);
+  const float inv_no = 1.f / ((float)a.counts[b * 4 + 1] + 1e-10f);
+  const float inv_ns = 1.f / ((float)a.counts[b * 4 + 2] + 1e-10f);
+  const float on_d = s_on[0] ? 1.f : 0.f, on_c = s_on[1] ? 1.f : 0.f, on_o = s_on[2] ? 1.f : 0.f;
+  const bool in = lane < S;
+  float l_d = 0.f, l_c = 0.f, l_o = 0.f;              // every lane carries the same per-ray values; lane 0's are used
+  for (int ray = blockIdx.x * 4 + warp; ray < a.R; ray += gridDim.x * 4) {
+    const long long pi = (long long)ray * S + lane;
+    float oc = 0.f, zz = 0.f, c0 = 0.f, c1 = 0.f, c2 = 0.f;
+    if (in) { oc = occ[pi]; zz = a.z[pi]; c0 = col[pi * 3]; c1 = col[pi * 3 + 1]; c2 = col[pi * 3 + 2]; }
+    const float om = 1.f - oc + 1e-10f;               // lanes past the ray: 1
+    float incl = om;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const float t = __shfl_up_sync(FULL, incl, d); if (lane >= d) incl *= t; }
+    float T = __shfl_up_sync(FULL, incl, 1);
+    if (lane == 0) T = 1.f;
+    const float w = oc * T;
+    const float D = warp_sum(w * zz), O = warp_sum(w), C0 = warp_sum(w * c0), C1 = warp_sum(w * c1), C2 = warp_sum(w * c2);
+    const float dz = zz - D;
+    const float V = warp_sum(w * dz * dz);
+    if (lane == 0) {
+      if (a.r_depth) a.r_depth[(size_t)b * a.R + ray] = D;
+      if (a.r_var) a.r_var[(size_t)b * a.R + ray] = V;
+      if (a.r_opacity) a.r_opacity[(size_t)b * a.R + ray] = O;
+      if (a.r_colour) { float* rc = a.r_colour + ((size_t)b * a.R + ray) * 3; rc[0] = C0; rc[1] = C1; rc[2] = C2; }
     }
-    float V = 0.f; T = 1.f;
-    for (int s = 0; s < S; ++s) {
-      const float oc = occ[pb + s], w = oc * T, dz = a.z[pb + s] - D;
-      V = fmaf(w, dz * dz, V);
-      T *= (1.f - oc + 1e-10f);
-    }
-    if (a.r_depth) a.r_depth[(size_t)b * a.R + ray] = D;
-    if (a.r_var) a.r_var[(size_t)b * a.R + ray] = V;
-    if (a.r_opacity) a.r_opacity[(size_t)b * a.R + ray] = O;
-    if (a.r_colour) { float* rc = a.r_colour + ((size_t)b * a.R + ray) * 3; rc[0] = C0; rc[1] = C1; rc[2] = C2; }
     const int sv = a.sem[ray];
     const float m_o = (sv != 0) ? 1.f : 0.f, m_s = (sv != 2) ? 1.f : 0.f, m_d = (a.mask[ray] != 0) ? m_o : 0.f;
     const float gd = a.gt_depth[ray];
     const float* gc = a.gt_colour + (size_t)ray * 3;
-    const float inv_nd = 1.f / ((float)a.counts[b * 4 + 0] + 1e-10f);
-    const float inv_no = 1.f / ((float)a.counts[b * 4 + 1] + 1e-10f);
-    const float inv_ns = 1.f / ((float)a.counts[b * 4 + 2] + 1e-10f);
     const float info = 1.f / (sqrtf(V) + 1e-4f);
-    const float on_d = s_on[0] ? 1.f : 0.f, on_c = s_on[1] ? 1.f : 0.f, on_o = s_on[2] ? 1.f : 0.f;
     const float e_d = D - gd, e_o = O - m_o, e_c0 = C0 - gc[0], e_c1 = C1 - gc[1], e_c2 = C2 - gc[2];
-    l_d = on_d * fabsf(e_d) * m_d * info * inv_nd;
-    l_c = on_c * (fabsf(e_c0) + fabsf(e_c1) + fabsf(e_c2)) * m_o * inv_no;
-    l_o = on_o * fabsf(e_o) * m_s * inv_ns;
+    l_d += on_d * fabsf(e_d) * m_d * info * inv_nd;
+    l_c += on_c * (fabsf(e_c0) + fabsf(e_c1) + fabsf(e_c2)) * m_o * inv_no;
+    l_o += on_o * fabsf(e_o) * m_s * inv_ns;
     if (a.backward) {
       const float gD = on_d * vmb_sign(e_d) * m_d * info * inv_nd;
       const float kc = on_c * a.cs * m_o * inv_no;
       const float gC0 = kc * vmb_sign(e_c0), gC1 = kc * vmb_sign(e_c1), gC2 = kc * vmb_sign(e_c2);
       const float gO = on_o * a.os * vmb_sign(e_o) * m_s * inv_ns;
-      // T_s backwards: recompute the exclusive products from the end
-      float Ts[32];
-      T = 1.f;
-      for (int s = 0; s < S; ++s) { Ts[s] = T; T *= (1.f - occ[pb + s] + 1e-10f); }
-      float suffix = 0.f;
-      for (int s = S - 1; s >= 0; --s) {
-        const float oc = occ[pb + s], w = oc * Ts[s];
-        const float c0 = col[(pb + s) * 3], c1 = col[(pb + s) * 3 + 1], c2 = col[(pb + s) * 3 + 2];
-        const float Gs = fmaf(gD, a.z[pb + s], fmaf(gC0, c0, fmaf(gC1, c1, fmaf(gC2, c2, gO))));
-        const float docc = Gs * Ts[s] - suffix / (1.f - oc + 1e-10f);
+      const float Gs = fmaf(gD, zz, fmaf(gC0, c0, fmaf(gC1, c1, fmaf(gC2, c2, gO))));
+      float sfx = Gs * w;                             // inclusive suffix sum of G_j w_j, then shifted to exclusive
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) { const float t = __shfl_down_sync(FULL, sfx, d); if (lane + d < 32) sfx += t; }
+      float suffix = __shfl_down_sync(FULL, sfx, 1);
+      if (lane == 31) suffix = 0.f;
+      const float docc = Gs * T - suffix / om;
+      if (in) {
         float4 dh;
         dh.x = 10.0f * docc * oc * (1.f - oc);
         dh.y = gC0 * w * c0 * (1.f - c0); dh.z = gC1 * w * c1 * (1.f - c1); dh.w = gC2 * w * c2 * (1.f - c2);
-        reinterpret_cast<float4*>(dhead)[pb + s] = dh;
-        suffix = fmaf(Gs, w, suffix);
+        reinterpret_cast<float4*>(dhead)[pi] = dh;
       }
     }
   }
-  l_d = warp_sum(l_d); l_c = warp_sum(l_c); l_o = warp_sum(l_o);
-  if ((threadIdx.x & 31) == 0) { atomicAdd(&s_loss[0], l_d); atomicAdd(&s_loss[1], l_c); atomicAdd(&s_loss[2], l_o); }
+  if (lane == 0) { atomicAdd(&s_loss[0], l_d); atomicAdd(&s_loss[1], l_c); atomicAdd(&s_loss[2], l_o); }
   __syncthreads();
   if (threadIdx.x < 3 && a.loss_terms) atomicAdd(a.loss_terms + b * 4 + threadIdx.x, s_loss[threadIdx.x]);
   if (threadIdx.x == 3 && a.loss_terms) atomicAdd(a.loss_terms + b * 4 + 3, s_loss[0] + a.cs * s_loss[1] + a.os * s_loss[2]);
@@ -316,14 +317,19 @@ __global__ void __launch_bounds__(128) k_lw_heads_bwd(const __half* __restrict__
   if (threadIdx.x >= 1 && threadIdx.x < 4) atomicAdd(G + L.o_boc + threadIdx.x - 1, s_b[threadIdx.x]);
 }
 
-// column sums of a [P][H] fp16 gradient block -> bias gradient (x 2^-8)
-__global__ void __launch_bounds__(256) k_lw_colsum(const __half* __restrict__ dY, long long np, int H, float* __restrict__ gb) {
+// column sums of a [P][H] fp16 gradient block -> bias gradient (x 2^-8); `rows` rows per block
+__global__ void __launch_bounds__(256) k_lw_colsum(const __half* __restrict__ dY, long long np, int H, int rows, float* __restrict__ gb) {
   const int c = threadIdx.x;
   if (c >= H) return;
-  const long long r0 = (long long)blockIdx.x * 512, r1 = min(np, r0 + 512);
-  float s = 0.f;
-  for (long long r = r0; r < r1; ++r) s += __half2float(dY[r * H + c]);
-  atomicAdd(gb + c, s * INV_LS);
+  const long long r0 = (long long)blockIdx.x * rows, r1 = min(np, r0 + rows);
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  long long r = r0;
+  for (; r + 3 < r1; r += 4) {
+    s0 += __half2float(dY[r * H + c]); s1 += __half2float(dY[(r + 1) * H + c]);
+    s2 += __half2float(dY[(r + 2) * H + c]); s3 += __half2float(dY[(r + 3) * H + c]);
+  }
+  for (; r < r1; ++r) s0 += __half2float(dY[r * H + c]);
+  atomicAdd(gb + c, ((s0 + s1) + (s2 + s3)) * INV_LS);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -445,13 +451,17 @@ static int step_object(Workspace& ws, const VmbLayout& L, const StepParams& sp, 
   ra.gt_colour = sp.gt_colour + (size_t)b * sp.gt_colour_stride; ra.sem = sp.sem + (size_t)b * sp.sem_stride;
   ra.mask = sp.mask + (size_t)b * sp.mask_stride; ra.counts = sp.counts; ra.cs = sp.cs; ra.os = sp.os; ra.backward = sp.backward;
   ra.loss_terms = sp.loss_terms; ra.r_depth = sp.r_depth; ra.r_var = sp.r_var; ra.r_colour = sp.r_colour; ra.r_opacity = sp.r_opacity;
-  k_lw_render<<<(sp.R + 127) / 128, 128, 0, st>>>(ra, ws.occ, ws.col, ws.dhead);
+  k_lw_render<<<std::min((sp.R + 3) / 4, 148 * 8), 128, 0, st>>>(ra, ws.occ, ws.col, ws.dhead);
   LW_TRY(cudaGetLastError());
   if (!sp.backward) return 0;
 
   // ---- backward ----
   k_lw_heads_bwd<H><<<nblk, 128, 0, st>>>(ws.XC, ws.dhead, Pb, L, np, ws.dYc, ws.dh16, ws.dalpha_s, G);
-  const int ksplit = 4096, zs = (int)((np + ksplit - 1) / ksplit);
+  // split over points: enough z slices that the widest weight-gradient GEMM (2 x 2 output tiles) fills the machine
+  // (148 SMs x 2 resident CTAs) at any point count, bounded below so a slice still amortises its pipeline fill
+  const int ksplit = (int)std::min<long long>(4096, std::max<long long>(512, ((np * 4 / 296 + BK - 1) / BK) * BK));
+  const int zs = (int)((np + ksplit - 1) / ksplit);
+  const int cs_rows = (int)std::max<long long>(64, (np + 591) / 592);       // bias column sums: ~4 blocks per SM
   // weight gradient: G[o*ldm + n] += sum_p dY[p][o] * X[p][n]   (A = dY^T, B = X, both MN-major, split over points)
   LW_TRY(ws.ensure_streams());
   cudaStream_t sd = ws.side;
@@ -492,7 +502,7 @@ static int step_object(Workspace& ws, const VmbLayout& L, const StepParams& sp, 
   // mid2
   LW_TRY(fork(1));
   LW_TRY(wgrad(ws.dYa, opX(ws.X3), H, L.o_Wm2, H, H, -1, -1));
-  k_lw_colsum<<<(int)((np + 511) / 512), 256, 0, sd>>>(ws.dYa, np, H, G + L.o_bm2);
+  k_lw_colsum<<<(int)((np + cs_rows - 1) / cs_rows), 256, 0, sd>>>(ws.dYa, np, H, cs_rows, G + L.o_bm2);
   LW_TRY(cudaEventRecord(ws.ev_side[0], sd));           // the side stream is done reading dYc (dY of color_linear) and dYa (dY4)
   LW_TRY(dgrad_gate(ws.dYa, off_m2(H), H, ws.X3, ws.dYb, nullptr, nullptr));                        // dY3 -> dYb
   // cat_layer
@@ -504,7 +514,7 @@ static int step_object(Workspace& ws, const VmbLayout& L, const StepParams& sp, 
   // mid1
   LW_TRY(fork(3));
   LW_TRY(wgrad(ws.dYa, opX(ws.X1), H, L.o_Wm1, H, H, -1, -1));
-  k_lw_colsum<<<(int)((np + 511) / 512), 256, 0, sd>>>(ws.dYa, np, H, G + L.o_bm1);
+  k_lw_colsum<<<(int)((np + cs_rows - 1) / cs_rows), 256, 0, sd>>>(ws.dYa, np, H, cs_rows, G + L.o_bm1);
   LW_TRY(dgrad_gate(ws.dYa, off_m1(H), H, ws.X1, ws.dYc, nullptr, nullptr));                        // dY1 -> dYc (free since color_linear)
   // in_layer
   LW_TRY(fork(4));

@@ -246,14 +246,14 @@ __global__ void k_loss_sum(const float* __restrict__ loss_terms, int B, float* _
 
 static int launch_adamw(vmb_handle* h, int n_obj, float* params, float* grads, float* m, float* v, void* image,
                         const float* loss_terms, int* status, const AdamScalars& q, float eps, int zero_grads,
-                        int* step_counter, cudaStream_t st) {
+                        int* step_counter, cudaStream_t st, const float* loss_sum_src = nullptr, float* loss_sum = nullptr) {
   if (h->L.stride < 1024) return fail(h, VMB_E_UNSUPPORTED, "vmb_adam: row pitch below one block");
   AdamParams p;
   memset(&p, 0, sizeof(p));
   p.n = (long long)n_obj * h->L.stride; p.stride = h->L.stride; p.P = h->L.P; p.B = n_obj;
   p.p = params; p.g = grads; p.m = m; p.v = v;
   p.image = (__half*)image; p.img_index = h->d_img_index; p.img_halves = h->img_halves;
-  p.loss_terms = loss_terms; p.status = status;
+  p.loss_terms = loss_terms; p.status = status; p.loss_sum_src = loss_sum_src; p.loss_sum = loss_sum;
   p.lr_wd = q.lr_wd; p.one_m_b1 = q.one_m_b1; p.b2 = q.b2; p.one_m_b2 = q.one_m_b2;
   p.step_counter = step_counter; p.ticket = h->d_ticket; p.lr = q.lr; p.b1 = q.b1; p.b2d = q.b2d;
   p.log_b1 = (float)std::log(q.b1); p.log_b2 = (float)std::log(q.b2d);
@@ -369,11 +369,12 @@ int vmb_step(vmb_handle* h, const vmb_step_args* a, void* stream) {
       return fail(h, VMB_E_ARG, "vmb_step: unknown impl");
     }
   }
-  if (a->loss_sum) { k_loss_sum<<<1, 32, 0, st>>>(a->loss_terms, a->n_obj, a->loss_sum); CUDA_TRY(h, cudaGetLastError()); }
-  if (a->fuse_adam)
+  if (a->fuse_adam)                                   // the AdamW launch also writes the step's scalar loss
     return launch_adamw(h, a->n_obj, const_cast<float*>(a->params), a->grads, a->exp_avg, a->exp_avg_sq,
                         (h->umma_ok || h->lw_ok) ? const_cast<void*>(a->image) : nullptr,
-                        a->guard_loss ? a->loss_terms : nullptr, a->status, q, a->eps, 1, a->step_counter, st);
+                        a->guard_loss ? a->loss_terms : nullptr, a->status, q, a->eps, 1, a->step_counter, st,
+                        a->loss_terms, a->loss_sum);
+  if (a->loss_sum) { k_loss_sum<<<1, 32, 0, st>>>(a->loss_terms, a->n_obj, a->loss_sum); CUDA_TRY(h, cudaGetLastError()); }
   return VMB_OK;
 }
 

@@ -67,7 +67,7 @@ class VmapEnsemble:
         self.scale = (sc.expand(n_obj) if sc.dim() == 0 else sc).to(dev).contiguous().clone()
         self.loss_terms = torch.zeros(n_obj, 4, **f32)
         self.status = torch.zeros(4, dtype=torch.int32, device=dev)
-        self.loss_sum = torch.zeros(1, **f32)              # the step's scalar loss (sum over objects), written by vmb_step
+        self.loss_ring = torch.zeros(4096, **f32)          # scalar loss of step t (sum over objects) lands in slot t % 4096
         self.step_count = 0
         # per-object step numbers on the device: graph replay needs them there, and objects that join a stack later
         # (update_vmap(..., keep_optimizer_state=True)) keep their own bias correction
@@ -204,13 +204,16 @@ class VmapEnsemble:
             _lib.check(self._handle, self.lib.vmb_adam(self._handle, C.byref(a), _stream()), "vmb_adam")
 
     def step(self, batch, impl: Optional[str] = None, loss_out: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """One optimisation step (train.py:293-326) in one library call.  Returns the summed loss as a device scalar:
-        a view of ``loss_out`` (a float32 device tensor the call writes into) or of ``self.loss_sum``.  No reduction
-        launch on the Python side: the step kernel's last CTA writes it."""
-        out = self.loss_sum if loss_out is None else loss_out
-        self.forward_backward(batch, impl=impl, fuse_adam=True, loss_out=out)
+        """One optimisation step (train.py:293-326) in one library call.  Returns the summed loss as a device scalar
+        with no reduction launch on the Python side: the step kernel's last CTA writes it into ``loss_out`` (a float32
+        device tensor) or, by default, into the next slot of a 4096-entry ring (so returned scalars stay valid -- and
+        distinct -- for the next 4095 steps; ``.item()`` / ``.clone()`` them to keep them longer)."""
+        if loss_out is None:
+            slot = self.step_count % self.loss_ring.numel()
+            loss_out = self.loss_ring[slot:slot + 1]
+        self.forward_backward(batch, impl=impl, fuse_adam=True, loss_out=loss_out)
         self.step_count += 1
-        return out.view(-1)[0]
+        return loss_out.view(-1)[0]
 
     def capture_step(self, batch, impl: Optional[str] = None) -> "torch.cuda.CUDAGraph":
         """Capture the step (one launch at hidden 32) on ``batch``'s (fixed) buffers into a CUDA graph; refill the buffers
