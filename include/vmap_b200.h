@@ -155,6 +155,9 @@ typedef struct vmb_adam_args {
                                instead of `step` and the kernel increments every counter, so that a captured
                                CUDA graph of the step can be replayed; per-object numbers let objects that
                                joined the stack later keep a correct bias correction       */
+  const float* grad_scale;  /* optional DEVICE float: gradients are multiplied by it on the way in (the upstream
+                               gradient autograd hands to `loss.backward()`, train.py:324), so the caller needs no
+                               scaling pass over `grads`                                                     */
 } vmb_adam_args;
 
 int vmb_adam(vmb_handle* h, const vmb_adam_args* a, void* stream);

@@ -51,7 +51,7 @@ class AdamArgs(C.Structure):
         ("image", _vp), ("loss_terms", _vp), ("status", _vp),
         ("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float),
         ("weight_decay", C.c_float), ("zero_grads", C.c_int),
-        ("step_counter", _vp),
+        ("step_counter", _vp), ("grad_scale", _vp),
     ]
 
 

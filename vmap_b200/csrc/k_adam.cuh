@@ -14,6 +14,7 @@ struct AdamParams {
   float* p; float* g; float* m; float* v;
   __half* image; const int* img_index; int img_halves;   // per-object image size in halves
   const float* loss_terms; int* status;
+  const float* grad_scale;    // optional device scalar multiplied into the gradients as they are read
   const float* loss_sum_src; float* loss_sum;   // optional: block 0 writes sum_b loss_sum_src[b][3] (the step's scalar loss)
   float lr_wd;                // 1 - lr*wd
   float one_m_b1, b2, one_m_b2;
@@ -86,6 +87,7 @@ __global__ void __launch_bounds__(256) k_adamw(AdamParams a) {
     }
   }
   if (i4 < a.n) {
+  if (a.grad_scale) { const float gs = *a.grad_scale; g.x *= gs; g.y *= gs; g.z *= gs; g.w *= gs; }
   const int b = (int)(i4 / a.stride);
   const float step_size = s_step_size[b - row0], bc2_sqrt = s_bc2_sqrt[b - row0];
   float* pp = &p.x; float* gg = &g.x; float* mm = &m.x; float* vv = &v.x;

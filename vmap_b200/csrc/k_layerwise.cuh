@@ -48,9 +48,9 @@ struct Workspace {
   long long cap_points = 0; int H = 0;
   __half *E = nullptr, *X1 = nullptr, *X2 = nullptr, *X3 = nullptr, *X4 = nullptr, *XC = nullptr;
   __half *dYa = nullptr, *dYb = nullptr, *dYc = nullptr, *dh16 = nullptr;
-  float *occ = nullptr, *col = nullptr, *dhead = nullptr, *dalpha_s = nullptr, *dE = nullptr;
+  float *dalpha_s = nullptr, *dE = nullptr;
   void release() {
-    void* ptrs[] = {E, X1, X2, X3, X4, XC, dYa, dYb, dYc, dh16, occ, col, dhead, dalpha_s, dE};
+    void* ptrs[] = {E, X1, X2, X3, X4, XC, dYa, dYb, dYc, dh16, dalpha_s, dE};
     for (void* q : ptrs) if (q) cudaFree(q);
     cudaStream_t keep_s = side; cudaEvent_t km[5], ks[2];
     for (int i = 0; i < 5; ++i) km[i] = ev_main[i];
@@ -93,7 +93,7 @@ struct Workspace {
     __half** hs[] = {&X1, &X2, &X3, &X4, &XC, &dYa, &dYb, &dYc};
     for (auto q : hs) al((void**)q, Pp * H_ * 2);
     al((void**)&dh16, Pp * 8 * 2);
-    al((void**)&occ, Pp * 4); al((void**)&col, Pp * 12); al((void**)&dhead, Pp * 16); al((void**)&dalpha_s, Pp * 4);
+    al((void**)&dalpha_s, Pp * 4);
     al((void**)&dE, Pp * EW * 4);
     if (e != cudaSuccess) { release(); return e; }
     cap_points = Pp; H = H_;
@@ -191,40 +191,74 @@ struct RenderArgs {
   const int* counts; float cs, os; int backward;
   float* loss_terms; float* r_depth; float* r_var; float* r_colour; float* r_opacity;
 };
-// One warp per ray, lane = sample (n_samples <= 32): coalesced loads, transmittance as a warp product scan, the
-// backward's suffix sum as a warp scan -- a ray's 32 samples cost a handful of shuffles instead of five serial passes.
-__global__ void __launch_bounds__(128) k_lw_render(RenderArgs a, const float* __restrict__ occ, const float* __restrict__ col,
-                                                   float* __restrict__ dhead) {
+// Heads + render + loss + head gradients in ONE kernel, one warp per ray, lane = sample (n_samples <= 32):
+//   forward   alpha / colour heads of the lane's point (the fc4 / hc rows are read once),
+//   render    transmittance as a warp product scan, the ray sums as warp reductions,
+//   backward  d(occupancy, colour) with the suffix sum as a warp scan, then dYc = relu'(hc) * (d_rawc @ W_oc)
+//             (fp16, x2^8), the scaled copies of d_alpha for the rank-1 term / the head wgrad GEMMs, and the bias
+//             gradients of the two heads.
+// Replaces three launches (heads, render, head gradients) and the round trip of occupancy / colour / dhead through HBM.
+template <int H>
+__global__ void __launch_bounds__(128) k_lw_heads_render(RenderArgs a, const __half* __restrict__ X4, const __half* __restrict__ XC,
+                                                         const float* __restrict__ P, VmbLayout L, __half* __restrict__ dYc,
+                                                         __half* __restrict__ dh16, float* __restrict__ dalpha_s,
+                                                         float* __restrict__ G) {
+  __shared__ float w[4 * H];                          // [0,H) out_alpha row, [H,4H) out_color rows
   __shared__ int s_on[3];
-  __shared__ float s_loss[3];
+  __shared__ float s_loss[3], s_b[4];
+  for (int i = threadIdx.x; i < H; i += 128) w[i] = P[L.o_Wa + i];
+  for (int i = threadIdx.x; i < 3 * H; i += 128) w[H + i] = P[L.o_Woc + i];
   if (threadIdx.x < 3) {
     int on = 1;
     for (int i = 0; i < a.B; ++i) on &= (a.counts[i * 4 + threadIdx.x] != 0);
     s_on[threadIdx.x] = on; s_loss[threadIdx.x] = 0.f;
   }
+  if (threadIdx.x < 4) s_b[threadIdx.x] = 0.f;
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, S = a.S, b = a.b;
   const unsigned FULL = 0xffffffffu;
+  const float b_a = P[L.o_ba], b_c0 = P[L.o_boc], b_c1 = P[L.o_boc + 1], b_c2 = P[L.o_boc + 2];
   const float inv_nd = 1.f / ((float)a.counts[b * 4 + 0] + 1e-10f);
   const float inv_no = 1.f / ((float)a.counts[b * 4 + 1] + 1e-10f);
   const float inv_ns = 1.f / ((float)a.counts[b * 4 + 2] + 1e-10f);
   const float on_d = s_on[0] ? 1.f : 0.f, on_c = s_on[1] ? 1.f : 0.f, on_o = s_on[2] ? 1.f : 0.f;
   const bool in = lane < S;
   float l_d = 0.f, l_c = 0.f, l_o = 0.f;              // every lane carries the same per-ray values; lane 0's are used
+  float sb0 = 0.f, sb1 = 0.f, sb2 = 0.f, sb3 = 0.f;   // this lane's share of the head bias gradients
   for (int ray = blockIdx.x * 4 + warp; ray < a.R; ray += gridDim.x * 4) {
     const long long pi = (long long)ray * S + lane;
     float oc = 0.f, zz = 0.f, c0 = 0.f, c1 = 0.f, c2 = 0.f;
-    if (in) { oc = occ[pi]; zz = a.z[pi]; c0 = col[pi * 3]; c1 = col[pi * 3 + 1]; c2 = col[pi * 3 + 2]; }
+    if (in) {
+      float ha = 0.f, h0 = 0.f, h1 = 0.f, h2 = 0.f;
+      const uint4* x4 = reinterpret_cast<const uint4*>(X4 + pi * H);
+      const uint4* xc = reinterpret_cast<const uint4*>(XC + pi * H);
+#pragma unroll 4
+      for (int q = 0; q < H / 8; ++q) {
+        const uint4 u = x4[q], v = xc[q];
+        const __half* hu = reinterpret_cast<const __half*>(&u);
+        const __half* hv = reinterpret_cast<const __half*>(&v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float f4 = __half2float(hu[j]), fc = __half2float(hv[j]);
+          const int o = q * 8 + j;
+          ha = fmaf(f4, w[o], ha);
+          h0 = fmaf(fc, w[H + o], h0); h1 = fmaf(fc, w[2 * H + o], h1); h2 = fmaf(fc, w[3 * H + o], h2);
+        }
+      }
+      oc = vmb_sigmoid((ha + b_a) * 10.0f);
+      c0 = vmb_sigmoid(h0 + b_c0); c1 = vmb_sigmoid(h1 + b_c1); c2 = vmb_sigmoid(h2 + b_c2);
+      zz = a.z[pi];
+    }
     const float om = 1.f - oc + 1e-10f;               // lanes past the ray: 1
     float incl = om;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) { const float t = __shfl_up_sync(FULL, incl, d); if (lane >= d) incl *= t; }
     float T = __shfl_up_sync(FULL, incl, 1);
     if (lane == 0) T = 1.f;
-    const float w = oc * T;
-    const float D = warp_sum(w * zz), O = warp_sum(w), C0 = warp_sum(w * c0), C1 = warp_sum(w * c1), C2 = warp_sum(w * c2);
+    const float wgt = oc * T;
+    const float D = warp_sum(wgt * zz), O = warp_sum(wgt), C0 = warp_sum(wgt * c0), C1 = warp_sum(wgt * c1), C2 = warp_sum(wgt * c2);
     const float dz = zz - D;
-    const float V = warp_sum(w * dz * dz);
+    const float V = warp_sum(wgt * dz * dz);
     if (lane == 0) {
       if (a.r_depth) a.r_depth[(size_t)b * a.R + ray] = D;
       if (a.r_var) a.r_var[(size_t)b * a.R + ray] = V;
@@ -240,81 +274,61 @@ __global__ void __launch_bounds__(128) k_lw_render(RenderArgs a, const float* __
     l_d += on_d * fabsf(e_d) * m_d * info * inv_nd;
     l_c += on_c * (fabsf(e_c0) + fabsf(e_c1) + fabsf(e_c2)) * m_o * inv_no;
     l_o += on_o * fabsf(e_o) * m_s * inv_ns;
-    if (a.backward) {
-      const float gD = on_d * vmb_sign(e_d) * m_d * info * inv_nd;
-      const float kc = on_c * a.cs * m_o * inv_no;
-      const float gC0 = kc * vmb_sign(e_c0), gC1 = kc * vmb_sign(e_c1), gC2 = kc * vmb_sign(e_c2);
-      const float gO = on_o * a.os * vmb_sign(e_o) * m_s * inv_ns;
-      const float Gs = fmaf(gD, zz, fmaf(gC0, c0, fmaf(gC1, c1, fmaf(gC2, c2, gO))));
-      float sfx = Gs * w;                             // inclusive suffix sum of G_j w_j, then shifted to exclusive
+    if (!a.backward) continue;
+    const float gD = on_d * vmb_sign(e_d) * m_d * info * inv_nd;
+    const float kc = on_c * a.cs * m_o * inv_no;
+    const float gC0 = kc * vmb_sign(e_c0), gC1 = kc * vmb_sign(e_c1), gC2 = kc * vmb_sign(e_c2);
+    const float gO = on_o * a.os * vmb_sign(e_o) * m_s * inv_ns;
+    const float Gs = fmaf(gD, zz, fmaf(gC0, c0, fmaf(gC1, c1, fmaf(gC2, c2, gO))));
+    float sfx = Gs * wgt;                             // inclusive suffix sum of G_j w_j, then shifted to exclusive
 #pragma unroll
-      for (int d = 1; d < 32; d <<= 1) { const float t = __shfl_down_sync(FULL, sfx, d); if (lane + d < 32) sfx += t; }
-      float suffix = __shfl_down_sync(FULL, sfx, 1);
-      if (lane == 31) suffix = 0.f;
+    for (int d = 1; d < 32; d <<= 1) { const float t = __shfl_down_sync(FULL, sfx, d); if (lane + d < 32) sfx += t; }
+    float suffix = __shfl_down_sync(FULL, sfx, 1);
+    if (lane == 31) suffix = 0.f;
+    if (in) {
       const float docc = Gs * T - suffix / om;
-      if (in) {
-        float4 dh;
-        dh.x = 10.0f * docc * oc * (1.f - oc);
-        dh.y = gC0 * w * c0 * (1.f - c0); dh.z = gC1 * w * c1 * (1.f - c1); dh.w = gC2 * w * c2 * (1.f - c2);
-        reinterpret_cast<float4*>(dhead)[pi] = dh;
+      float4 dh;                                      // d(loss) / d(raw alpha, raw colour) of this point
+      dh.x = 10.0f * docc * oc * (1.f - oc);
+      dh.y = gC0 * wgt * c0 * (1.f - c0); dh.z = gC1 * wgt * c1 * (1.f - c1); dh.w = gC2 * wgt * c2 * (1.f - c2);
+      sb0 += dh.x; sb1 += dh.y; sb2 += dh.z; sb3 += dh.w;
+      dalpha_s[pi] = LS * dh.x;
+      __half2 h01 = __floats2half2_rn(fminf(fmaxf(LS * dh.x, -60000.f), 60000.f), fminf(fmaxf(LS * dh.y, -60000.f), 60000.f));
+      __half2 h23 = __floats2half2_rn(fminf(fmaxf(LS * dh.z, -60000.f), 60000.f), fminf(fmaxf(LS * dh.w, -60000.f), 60000.f));
+      reinterpret_cast<uint4*>(dh16)[pi] = make_uint4(*reinterpret_cast<uint32_t*>(&h01), *reinterpret_cast<uint32_t*>(&h23), 0u, 0u);
+      const uint4* xc = reinterpret_cast<const uint4*>(XC + pi * H);      // second pass over the hc row: L1-resident
+      uint4* out = reinterpret_cast<uint4*>(dYc + pi * H);
+      const float d0 = LS * dh.y, d1 = LS * dh.z, d2 = LS * dh.w;
+#pragma unroll 4
+      for (int q = 0; q < H / 8; ++q) {
+        const uint4 v = xc[q];
+        const __half* hv = reinterpret_cast<const __half*>(&v);
+        uint32_t r[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int o = q * 8 + 2 * j;
+          float x0 = fmaf(d2, w[3 * H + o], fmaf(d1, w[2 * H + o], d0 * w[H + o]));
+          float x1 = fmaf(d2, w[3 * H + o + 1], fmaf(d1, w[2 * H + o + 1], d0 * w[H + o + 1]));
+          x0 = (__half2float(hv[2 * j]) > 0.f) ? fminf(fmaxf(x0, -60000.f), 60000.f) : 0.f;
+          x1 = (__half2float(hv[2 * j + 1]) > 0.f) ? fminf(fmaxf(x1, -60000.f), 60000.f) : 0.f;
+          __half2 hh = __floats2half2_rn(x0, x1);
+          r[j] = *reinterpret_cast<uint32_t*>(&hh);
+        }
+        out[q] = make_uint4(r[0], r[1], r[2], r[3]);
       }
     }
   }
   if (lane == 0) { atomicAdd(&s_loss[0], l_d); atomicAdd(&s_loss[1], l_c); atomicAdd(&s_loss[2], l_o); }
+  if (a.backward) {
+    sb0 = warp_sum(sb0); sb1 = warp_sum(sb1); sb2 = warp_sum(sb2); sb3 = warp_sum(sb3);
+    if (lane == 0) { atomicAdd(&s_b[0], sb0); atomicAdd(&s_b[1], sb1); atomicAdd(&s_b[2], sb2); atomicAdd(&s_b[3], sb3); }
+  }
   __syncthreads();
   if (threadIdx.x < 3 && a.loss_terms) atomicAdd(a.loss_terms + b * 4 + threadIdx.x, s_loss[threadIdx.x]);
   if (threadIdx.x == 3 && a.loss_terms) atomicAdd(a.loss_terms + b * 4 + 3, s_loss[0] + a.cs * s_loss[1] + a.os * s_loss[2]);
-}
-
-// ---------------------------------------------------------------------------------------------
-// head gradients: dYc = relu'(hc) * (d_rawc @ W_oc) (fp16, x2^8); scaled copies of d_alpha for the rank-1
-// term / the head wgrad GEMMs; bias gradients of the two heads
-// ---------------------------------------------------------------------------------------------
-template <int H>
-__global__ void __launch_bounds__(128) k_lw_heads_bwd(const __half* __restrict__ XC, const float* __restrict__ dhead,
-                                                      const float* __restrict__ P, VmbLayout L, long long np,
-                                                      __half* __restrict__ dYc, __half* __restrict__ dh16,
-                                                      float* __restrict__ dalpha_s, float* __restrict__ G) {
-  __shared__ float w[3 * H];
-  __shared__ float s_b[4];
-  for (int i = threadIdx.x; i < 3 * H; i += 128) w[i] = P[L.o_Woc + i];
-  if (threadIdx.x < 4) s_b[threadIdx.x] = 0.f;
-  __syncthreads();
-  const long long p = (long long)blockIdx.x * 128 + threadIdx.x;
-  float4 dh = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (p < np) {
-    dh = reinterpret_cast<const float4*>(dhead)[p];
-    dalpha_s[p] = LS * dh.x;
-    __half2 h01 = __floats2half2_rn(fminf(fmaxf(LS * dh.x, -60000.f), 60000.f), fminf(fmaxf(LS * dh.y, -60000.f), 60000.f));
-    __half2 h23 = __floats2half2_rn(fminf(fmaxf(LS * dh.z, -60000.f), 60000.f), fminf(fmaxf(LS * dh.w, -60000.f), 60000.f));
-    reinterpret_cast<uint4*>(dh16)[p] = make_uint4(*reinterpret_cast<uint32_t*>(&h01), *reinterpret_cast<uint32_t*>(&h23), 0u, 0u);
-    const uint4* xc = reinterpret_cast<const uint4*>(XC + p * H);
-    uint4* out = reinterpret_cast<uint4*>(dYc + p * H);
-    const float d0 = LS * dh.y, d1 = LS * dh.z, d2 = LS * dh.w;
-#pragma unroll 4
-    for (int q = 0; q < H / 8; ++q) {
-      const uint4 v = xc[q];
-      const __half* hv = reinterpret_cast<const __half*>(&v);
-      uint32_t r[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int o = q * 8 + 2 * j;
-        float a = fmaf(d2, w[2 * H + o], fmaf(d1, w[H + o], d0 * w[o]));
-        float bq = fmaf(d2, w[2 * H + o + 1], fmaf(d1, w[H + o + 1], d0 * w[o + 1]));
-        a = (__half2float(hv[2 * j]) > 0.f) ? fminf(fmaxf(a, -60000.f), 60000.f) : 0.f;
-        bq = (__half2float(hv[2 * j + 1]) > 0.f) ? fminf(fmaxf(bq, -60000.f), 60000.f) : 0.f;
-        __half2 hh = __floats2half2_rn(a, bq);
-        r[j] = *reinterpret_cast<uint32_t*>(&hh);
-      }
-      out[q] = make_uint4(r[0], r[1], r[2], r[3]);
-    }
+  if (a.backward && G) {
+    if (threadIdx.x == 32) atomicAdd(G + L.o_ba, s_b[0]);
+    if (threadIdx.x >= 33 && threadIdx.x < 36) atomicAdd(G + L.o_boc + threadIdx.x - 33, s_b[threadIdx.x - 32]);
   }
-  // bias gradients: db_a = sum d_araw, db_oc[c] = sum d_rawc[c]
-  float s0 = warp_sum(dh.x), s1 = warp_sum(dh.y), s2 = warp_sum(dh.z), s3 = warp_sum(dh.w);
-  if ((threadIdx.x & 31) == 0) { atomicAdd(&s_b[0], s0); atomicAdd(&s_b[1], s1); atomicAdd(&s_b[2], s2); atomicAdd(&s_b[3], s3); }
-  __syncthreads();
-  if (threadIdx.x == 0) atomicAdd(G + L.o_ba, s_b[0]);
-  if (threadIdx.x >= 1 && threadIdx.x < 4) atomicAdd(G + L.o_boc + threadIdx.x - 1, s_b[threadIdx.x]);
 }
 
 // column sums of a [P][H] fp16 gradient block -> bias gradient (x 2^-8); `rows` rows per block
@@ -444,19 +458,18 @@ static int step_object(Workspace& ws, const VmbLayout& L, const StepParams& sp, 
     LW_TRY(cudaGetLastError());
     return 0;
   }
-  k_lw_heads<H><<<nblk, 128, 0, st>>>(ws.X4, ws.XC, Pb, L, np, ws.occ, ws.col, 0);
   RenderArgs ra;
   ra.b = b; ra.R = sp.R; ra.S = sp.S; ra.B = sp.B;
   ra.z = sp.z + (size_t)b * sp.z_stride; ra.gt_depth = sp.gt_depth + (size_t)b * sp.gt_depth_stride;
   ra.gt_colour = sp.gt_colour + (size_t)b * sp.gt_colour_stride; ra.sem = sp.sem + (size_t)b * sp.sem_stride;
   ra.mask = sp.mask + (size_t)b * sp.mask_stride; ra.counts = sp.counts; ra.cs = sp.cs; ra.os = sp.os; ra.backward = sp.backward;
   ra.loss_terms = sp.loss_terms; ra.r_depth = sp.r_depth; ra.r_var = sp.r_var; ra.r_colour = sp.r_colour; ra.r_opacity = sp.r_opacity;
-  k_lw_render<<<std::min((sp.R + 3) / 4, 148 * 8), 128, 0, st>>>(ra, ws.occ, ws.col, ws.dhead);
+  // heads + render + loss (+ head gradients when training) in one launch
+  k_lw_heads_render<H><<<std::min((sp.R + 3) / 4, 148 * 8), 128, 0, st>>>(ra, ws.X4, ws.XC, Pb, L, ws.dYc, ws.dh16, ws.dalpha_s, G);
   LW_TRY(cudaGetLastError());
   if (!sp.backward) return 0;
 
   // ---- backward ----
-  k_lw_heads_bwd<H><<<nblk, 128, 0, st>>>(ws.XC, ws.dhead, Pb, L, np, ws.dYc, ws.dh16, ws.dalpha_s, G);
   // split over points: enough z slices that the widest weight-gradient GEMM (2 x 2 output tiles) fills the machine
   // (148 SMs x 2 resident CTAs) at any point count, bounded below so a slice still amortises its pipeline fill
   const int ksplit = (int)std::min<long long>(4096, std::max<long long>(512, ((np * 4 / 296 + BK - 1) / BK) * BK));

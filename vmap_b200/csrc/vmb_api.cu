@@ -246,14 +246,15 @@ __global__ void k_loss_sum(const float* __restrict__ loss_terms, int B, float* _
 
 static int launch_adamw(vmb_handle* h, int n_obj, float* params, float* grads, float* m, float* v, void* image,
                         const float* loss_terms, int* status, const AdamScalars& q, float eps, int zero_grads,
-                        int* step_counter, cudaStream_t st, const float* loss_sum_src = nullptr, float* loss_sum = nullptr) {
+                        int* step_counter, cudaStream_t st, const float* loss_sum_src = nullptr, float* loss_sum = nullptr,
+                        const float* grad_scale = nullptr) {
   if (h->L.stride < 1024) return fail(h, VMB_E_UNSUPPORTED, "vmb_adam: row pitch below one block");
   AdamParams p;
   memset(&p, 0, sizeof(p));
   p.n = (long long)n_obj * h->L.stride; p.stride = h->L.stride; p.P = h->L.P; p.B = n_obj;
   p.p = params; p.g = grads; p.m = m; p.v = v;
   p.image = (__half*)image; p.img_index = h->d_img_index; p.img_halves = h->img_halves;
-  p.loss_terms = loss_terms; p.status = status; p.loss_sum_src = loss_sum_src; p.loss_sum = loss_sum;
+  p.loss_terms = loss_terms; p.status = status; p.loss_sum_src = loss_sum_src; p.loss_sum = loss_sum; p.grad_scale = grad_scale;
   p.lr_wd = q.lr_wd; p.one_m_b1 = q.one_m_b1; p.b2 = q.b2; p.one_m_b2 = q.one_m_b2;
   p.step_counter = step_counter; p.ticket = h->d_ticket; p.lr = q.lr; p.b1 = q.b1; p.b2d = q.b2d;
   p.log_b1 = (float)std::log(q.b1); p.log_b2 = (float)std::log(q.b2d);
@@ -415,7 +416,7 @@ int vmb_adam(vmb_handle* h, const vmb_adam_args* a, void* stream) {
   if (a->image && !h->umma_ok && !h->lw_ok) return fail(h, VMB_E_UNSUPPORTED, "vmb_adam: no fp16 image for this hidden size");
   const AdamScalars q = adam_scalars(a->lr, a->beta1, a->beta2, a->weight_decay, a->step);
   return launch_adamw(h, a->n_obj, a->params, a->grads, a->exp_avg, a->exp_avg_sq, a->image, a->loss_terms, a->status, q,
-                      a->eps, a->zero_grads, a->step_counter, (cudaStream_t)stream);
+                      a->eps, a->zero_grads, a->step_counter, (cudaStream_t)stream, nullptr, nullptr, a->grad_scale);
 }
 
 int vmb_build_image(vmb_handle* h, int n_obj, const float* params, void* image, void* stream) {

@@ -10,6 +10,7 @@ forward+loss+backward, ordered gradient reduction and AdamW all inside ``vmb_ste
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes as C
 import os
 from typing import Dict, Optional
@@ -27,6 +28,17 @@ class LossExplode(RuntimeError):
 
 def _ptr(t: Optional[torch.Tensor]):
     return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def rows_dense(t: torch.Tensor) -> bool:
+    """True when every t[i] is a dense block (what ``t[i].is_contiguous()`` says, without building the view)."""
+    expect = 1
+    shape, stride = t.shape, t.stride()
+    for d in range(t.dim() - 1, 0, -1):
+        if shape[d] != 1 and stride[d] != expect:
+            return False
+        expect *= shape[d]
+    return True
 
 
 def _stream():
@@ -67,6 +79,8 @@ class VmapEnsemble:
         self.scale = (sc.expand(n_obj) if sc.dim() == 0 else sc).to(dev).contiguous().clone()
         self.loss_terms = torch.zeros(n_obj, 4, **f32)
         self.status = torch.zeros(4, dtype=torch.int32, device=dev)
+        self._grad_scale = self._grad_scale_held = None
+        self.loss_calls = 0                                 # step_batch_loss launches so far (their slot in loss_ring)
         self.loss_ring = torch.zeros(4096, **f32)          # scalar loss of step t (sum over objects) lands in slot t % 4096
         self.step_count = 0
         # per-object step numbers on the device: graph replay needs them there, and objects that join a stack later
@@ -117,6 +131,12 @@ class VmapEnsemble:
                 _lib.check(self._handle, self.lib.vmb_build_image(self._handle, self.n_obj, _ptr(self.params),
                                                                   _ptr(self.image), _stream()), "vmb_build_image")
 
+    def _on_device(self):
+        """Context that makes ``self.device`` current; free when it already is (the common single-GPU case)."""
+        if torch.cuda.current_device() == self.device.index:
+            return contextlib.nullcontext()
+        return torch.cuda.device(self.device)
+
     # ---- kernels ----------------------------------------------------------------------------
     def _step_args(self, batch, backward: bool, outputs=None, impl: Optional[str] = None, counts=None,
                    fuse_adam: bool = False, guard_loss: bool = True, loss_out: Optional[torch.Tensor] = None):
@@ -128,8 +148,8 @@ class VmapEnsemble:
             assert t.dtype == dt and t.device == self.device
         assert sem.dtype == torch.uint8 and md.dtype in (torch.bool, torch.uint8)
         # per-object slices of a bigger tensor are fine as long as each object's block is dense
-        for t, inner in ((pcs, R * S * 3), (z, R * S), (gd, R), (gc, R * 3), (sem, R), (md, R)):
-            assert t[0].is_contiguous(), "per-object block must be contiguous"
+        for t in (pcs, z, gd, gc, sem, md):
+            assert rows_dense(t), "per-object block must be contiguous"
         a = _lib.StepArgs()
         a.n_obj, a.n_rays, a.n_samples = B, R, S
         a.impl = _lib.VMB_IMPL[impl or self.impl]
@@ -172,7 +192,7 @@ class VmapEnsemble:
                     ev.record()                  # torch creates the CUDA event lazily
             a.k1_start_event = C.c_void_p(k1_events[0].cuda_event)
             a.k1_stop_event = C.c_void_p(k1_events[1].cuda_event)
-        with torch.cuda.device(self.device):
+        with self._on_device():
             _lib.check(self._handle, self.lib.vmb_step(self._handle, C.byref(a), _stream()), "vmb_step")
 
     def mask_counts(self, batch) -> torch.Tensor:
@@ -200,7 +220,10 @@ class VmapEnsemble:
         a.status = _ptr(self.status)
         a.lr, a.beta1, a.beta2, a.eps = self.lr, self.betas[0], self.betas[1], self.eps
         a.weight_decay, a.zero_grads = self.weight_decay, 1
-        with torch.cuda.device(self.device):
+        if self._grad_scale is not None:                      # upstream gradient of loss.backward(), applied by the kernel
+            a.grad_scale = _ptr(self._grad_scale)
+        self._grad_scale_held, self._grad_scale = self._grad_scale, None     # keep it alive past the asynchronous launch
+        with self._on_device():
             _lib.check(self._handle, self.lib.vmb_adam(self._handle, C.byref(a), _stream()), "vmb_adam")
 
     def step(self, batch, impl: Optional[str] = None, loss_out: Optional[torch.Tensor] = None) -> torch.Tensor:

@@ -109,18 +109,22 @@ class _FusedLoss(torch.autograd.Function):
     """Scalar loss whose gradient already sits in ``ens.grads`` (K1 computed it)."""
 
     @staticmethod
-    def forward(ctx, anchor, ens):
+    def forward(ctx, anchor, ens, total):
         ctx.ens = ens
-        return ens.loss_terms[:, 3].sum()
+        return total.detach().view(())
 
     @staticmethod
     def backward(ctx, g):
-        ctx.ens.grads.mul_(g)            # d(total)/d(this loss); 1 for loss.backward()
-        return None, None
+        # d(total)/d(this loss) (1 for loss.backward()): handed to the AdamW launch, which multiplies the gradients
+        # by it as it reads them -- no pass over ens.grads here
+        ens = ctx.ens
+        ens._grad_scale = g if ens._grad_scale is None else ens._grad_scale * g
+        return None, None, None
 
 
-def fused_loss(ens) -> torch.Tensor:
+def fused_loss(ens, total: torch.Tensor) -> torch.Tensor:
+    """``total``: the one-element device tensor the step launch wrote the scalar loss into."""
     if getattr(ens, "_anchor", None) is None:
         ens._anchor = torch.zeros((), device=ens.device, requires_grad=True)
     _DIRTY.add(ens)
-    return _FusedLoss.apply(ens._anchor, ens)
+    return _FusedLoss.apply(ens._anchor, ens, total)

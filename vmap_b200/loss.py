@@ -5,6 +5,7 @@ from __future__ import annotations
 
 import torch
 
+from .ensemble import rows_dense
 from .lazy import LazyHead, fused_loss
 
 
@@ -28,10 +29,13 @@ def step_batch_loss(alpha, color, gt_depth, gt_color, sem_labels, mask_depth, z_
         "sem": lead(sem_labels, 2), "mask_depth": lead(mask_depth, 2),
     }
     assert batch["pcs"].shape[0] == B, "object count differs from the stacked ensemble"
-    batch = {k: (v if v[0].is_contiguous() else v.contiguous()) for k, v in batch.items()}
+    batch = {k: (v if rows_dense(v) else v.contiguous()) for k, v in batch.items()}
     if batch["sem"].dtype != torch.uint8:
         batch["sem"] = batch["sem"].to(torch.uint8)
     ens.colour_scaling, ens.opacity_scaling = float(color_scaling), float(opacity_scaling)
-    ens.forward_backward(batch)
+    slot = ens.loss_calls % ens.loss_ring.numel()      # the launch writes the scalar loss itself (no reduction launch)
+    ens.loss_calls += 1
+    total = ens.loss_ring[slot:slot + 1]
+    ens.forward_backward(batch, loss_out=total)
     ens._last_batch = batch                 # inputs must outlive the asynchronous launch
-    return fused_loss(ens), None
+    return fused_loss(ens, total), None

@@ -30,6 +30,7 @@ class FusedAdamW:
     def zero_grad(self, set_to_none=True):
         for ens in list(_DIRTY):             # gradients produced but never stepped
             ens.grads.zero_()
+            ens._grad_scale = None
         _DIRTY.clear()
 
 
