@@ -201,6 +201,32 @@ __device__ __forceinline__ void epi_chunk(const GemmArgs& g, float (&v)[32], int
         if (nb + j < g.N) o[j] = (g.accumulate ? o[j] : 0.f) + v[j] * g.scale;
       }
     }
+  } else if (stage && g.ldgn == 1) {
+    // EPI_ATOMIC, unit column stride: a thread owns a ROW, so direct atomics would hit 32 different rows (32 L2
+    // transactions) per instruction.  Transpose 16 columns at a time through the per-warp tile ([32][17] floats) so
+    // each reduction instruction covers two rows x 16 consecutive floats.
+    float* stf = reinterpret_cast<float*>(stage);
+    const int c = lane & 15, rsub = lane >> 4;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) stf[lane * 17 + j] = v[half * 16 + j] * g.scale;
+      __syncwarp();
+      const int n = nb + half * 16 + c;
+      const bool n_in = n >= g.n_lo && n < g.n_valid, n_bias = n == g.ones_col && g.gbias != nullptr;
+      if (n_in || n_bias) {
+#pragma unroll 4
+        for (int r2 = 0; r2 < 16; ++r2) {
+          const int r = r2 * 2 + rsub, mrow = m_base + r;
+          if (mrow < g.M) {
+            const float val = stf[r * 17 + c];
+            if (n_in) atomicAdd(g.gdst + (size_t)mrow * g.ldgd + n, val);
+            else atomicAdd(g.gbias + mrow, val);
+          }
+        }
+      }
+      __syncwarp();
+    }
   } else if (m < g.M) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
@@ -315,7 +341,7 @@ k_gemm_umma(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ C
       ptx::tmem_ld32(taddr + c32, v);
       ptx::tmem_ld_wait();
       epi_chunk<EPI>(g, v, m0 + warp * 32, tid & 31, n0 + c32, g.bias,
-                     (EPI == EPI_RELU_F16 || EPI == EPI_GATE_F16) ? smem + NSTAGE * STAGE_BYTES + 1024 + warp * EPI_STAGE_F16 : nullptr);
+                     (EPI == EPI_RELU_F16 || EPI == EPI_GATE_F16 || EPI == EPI_ATOMIC) ? smem + NSTAGE * STAGE_BYTES + 1024 + warp * EPI_STAGE_F16 : nullptr);
     }
     ptx::tc_fence_before();
     ptx::mbar_arrive(&tempty[acc]);            // this thread has drained its lanes of the accumulator

@@ -198,14 +198,24 @@ struct RenderArgs {
 //             (fp16, x2^8), the scaled copies of d_alpha for the rank-1 term / the head wgrad GEMMs, and the bias
 //             gradients of the two heads.
 // Replaces three launches (heads, render, head gradients) and the round trip of occupancy / colour / dhead through HBM.
+// A warp first stages its ray's fc4 / hc rows in shared memory with coalesced 16 B asynchronous copies (a lane walking
+// its own 2H-byte row straight from global memory is a chain of dependent L2 round trips); the row pitch of 2H + 16 B
+// makes the per-lane 16 B reads conflict-free.
+template <int H> constexpr int hr_pitch() { return H * 2 + 16; }
+template <int H> constexpr int hr_smem() { return 4 * 2 * 32 * hr_pitch<H>(); }     // 4 warps x {fc4, hc} x 32 rows
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(ptx::smem_u32(dst)), "l"(src) : "memory");
+}
 template <int H>
 __global__ void __launch_bounds__(128) k_lw_heads_render(RenderArgs a, const __half* __restrict__ X4, const __half* __restrict__ XC,
                                                          const float* __restrict__ P, VmbLayout L, __half* __restrict__ dYc,
                                                          __half* __restrict__ dh16, float* __restrict__ dalpha_s,
                                                          float* __restrict__ G) {
+  extern __shared__ __align__(16) unsigned char hr_rows[];
   __shared__ float w[4 * H];                          // [0,H) out_alpha row, [H,4H) out_color rows
   __shared__ int s_on[3];
   __shared__ float s_loss[3], s_b[4];
+  constexpr int PITCH = hr_pitch<H>(), LPR = H / 8, RPP = 32 / LPR;      // lanes per row, rows per copy pass
   for (int i = threadIdx.x; i < H; i += 128) w[i] = P[L.o_Wa + i];
   for (int i = threadIdx.x; i < 3 * H; i += 128) w[H + i] = P[L.o_Woc + i];
   if (threadIdx.x < 3) {
@@ -223,15 +233,28 @@ __global__ void __launch_bounds__(128) k_lw_heads_render(RenderArgs a, const __h
   const float inv_ns = 1.f / ((float)a.counts[b * 4 + 2] + 1e-10f);
   const float on_d = s_on[0] ? 1.f : 0.f, on_c = s_on[1] ? 1.f : 0.f, on_o = s_on[2] ? 1.f : 0.f;
   const bool in = lane < S;
+  unsigned char* s4 = hr_rows + warp * (2 * 32 * PITCH);       // this warp's fc4 rows, then its hc rows
+  unsigned char* sc = s4 + 32 * PITCH;
   float l_d = 0.f, l_c = 0.f, l_o = 0.f;              // every lane carries the same per-ray values; lane 0's are used
   float sb0 = 0.f, sb1 = 0.f, sb2 = 0.f, sb3 = 0.f;   // this lane's share of the head bias gradients
   for (int ray = blockIdx.x * 4 + warp; ray < a.R; ray += gridDim.x * 4) {
-    const long long pi = (long long)ray * S + lane;
+    const long long pb = (long long)ray * S, pi = pb + lane;
+    __syncwarp();                                     // the previous ray's rows are no longer read
+#pragma unroll 4
+    for (int r0 = 0; r0 < S; r0 += RPP) {
+      const int r = r0 + lane / LPR, cq = lane % LPR;
+      if (r < S) {
+        cp_async16(s4 + r * PITCH + cq * 16, X4 + (pb + r) * H + cq * 8);
+        cp_async16(sc + r * PITCH + cq * 16, XC + (pb + r) * H + cq * 8);
+      }
+    }
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+    __syncwarp();
     float oc = 0.f, zz = 0.f, c0 = 0.f, c1 = 0.f, c2 = 0.f;
     if (in) {
       float ha = 0.f, h0 = 0.f, h1 = 0.f, h2 = 0.f;
-      const uint4* x4 = reinterpret_cast<const uint4*>(X4 + pi * H);
-      const uint4* xc = reinterpret_cast<const uint4*>(XC + pi * H);
+      const uint4* x4 = reinterpret_cast<const uint4*>(s4 + lane * PITCH);
+      const uint4* xc = reinterpret_cast<const uint4*>(sc + lane * PITCH);
 #pragma unroll 4
       for (int q = 0; q < H / 8; ++q) {
         const uint4 u = x4[q], v = xc[q];
@@ -295,7 +318,7 @@ __global__ void __launch_bounds__(128) k_lw_heads_render(RenderArgs a, const __h
       __half2 h01 = __floats2half2_rn(fminf(fmaxf(LS * dh.x, -60000.f), 60000.f), fminf(fmaxf(LS * dh.y, -60000.f), 60000.f));
       __half2 h23 = __floats2half2_rn(fminf(fmaxf(LS * dh.z, -60000.f), 60000.f), fminf(fmaxf(LS * dh.w, -60000.f), 60000.f));
       reinterpret_cast<uint4*>(dh16)[pi] = make_uint4(*reinterpret_cast<uint32_t*>(&h01), *reinterpret_cast<uint32_t*>(&h23), 0u, 0u);
-      const uint4* xc = reinterpret_cast<const uint4*>(XC + pi * H);      // second pass over the hc row: L1-resident
+      const uint4* xc = reinterpret_cast<const uint4*>(sc + lane * PITCH);   // second pass over the staged hc row
       uint4* out = reinterpret_cast<uint4*>(dYc + pi * H);
       const float d0 = LS * dh.y, d1 = LS * dh.z, d2 = LS * dh.w;
 #pragma unroll 4
@@ -465,7 +488,17 @@ static int step_object(Workspace& ws, const VmbLayout& L, const StepParams& sp, 
   ra.mask = sp.mask + (size_t)b * sp.mask_stride; ra.counts = sp.counts; ra.cs = sp.cs; ra.os = sp.os; ra.backward = sp.backward;
   ra.loss_terms = sp.loss_terms; ra.r_depth = sp.r_depth; ra.r_var = sp.r_var; ra.r_colour = sp.r_colour; ra.r_opacity = sp.r_opacity;
   // heads + render + loss (+ head gradients when training) in one launch
-  k_lw_heads_render<H><<<std::min((sp.R + 3) / 4, 148 * 8), 128, 0, st>>>(ra, ws.X4, ws.XC, Pb, L, ws.dYc, ws.dh16, ws.dalpha_s, G);
+  {
+    static bool attr_set[64] = {};
+    int dev = 0; cudaGetDevice(&dev);
+    if (!attr_set[dev & 63]) {
+      LW_TRY(cudaFuncSetAttribute(k_lw_heads_render<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, hr_smem<H>()));
+      attr_set[dev & 63] = true;
+    }
+  }
+  const int hr_per_sm = std::max(1, std::min(8, (int)(220 * 1024 / (hr_smem<H>() + 8 * 1024))));
+  k_lw_heads_render<H><<<std::min((sp.R + 3) / 4, 148 * hr_per_sm), 128, hr_smem<H>(), st>>>(ra, ws.X4, ws.XC, Pb, L, ws.dYc, ws.dh16,
+                                                                                          ws.dalpha_s, G);
   LW_TRY(cudaGetLastError());
   if (!sp.backward) return 0;
 
