@@ -198,11 +198,12 @@ struct RenderArgs {
 //             (fp16, x2^8), the scaled copies of d_alpha for the rank-1 term / the head wgrad GEMMs, and the bias
 //             gradients of the two heads.
 // Replaces three launches (heads, render, head gradients) and the round trip of occupancy / colour / dhead through HBM.
-// A warp first stages its ray's fc4 / hc rows in shared memory with coalesced 16 B asynchronous copies (a lane walking
-// its own 2H-byte row straight from global memory is a chain of dependent L2 round trips); the row pitch of 2H + 16 B
-// makes the per-lane 16 B reads conflict-free.
+// A warp stages its ray's fc4 rows, then its hc rows, in ONE shared-memory buffer with coalesced 16 B asynchronous
+// copies (a lane walking its own 2H-byte row straight from global memory is a chain of dependent L2 round trips); the
+// row pitch of 2H + 16 B makes the per-lane 16 B reads conflict-free, and one buffer per warp keeps three blocks
+// resident per SM at H = 256 so the copies of one warp hide behind the arithmetic of the others.
 template <int H> constexpr int hr_pitch() { return H * 2 + 16; }
-template <int H> constexpr int hr_smem() { return 4 * 2 * 32 * hr_pitch<H>(); }     // 4 warps x {fc4, hc} x 32 rows
+template <int H> constexpr int hr_smem() { return 4 * 32 * hr_pitch<H>(); }         // 4 warps x 32 rows (fc4, then hc)
 __device__ __forceinline__ void cp_async16(void* dst, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(ptx::smem_u32(dst)), "l"(src) : "memory");
 }
@@ -233,38 +234,50 @@ __global__ void __launch_bounds__(128) k_lw_heads_render(RenderArgs a, const __h
   const float inv_ns = 1.f / ((float)a.counts[b * 4 + 2] + 1e-10f);
   const float on_d = s_on[0] ? 1.f : 0.f, on_c = s_on[1] ? 1.f : 0.f, on_o = s_on[2] ? 1.f : 0.f;
   const bool in = lane < S;
-  unsigned char* s4 = hr_rows + warp * (2 * 32 * PITCH);       // this warp's fc4 rows, then its hc rows
-  unsigned char* sc = s4 + 32 * PITCH;
+  unsigned char* srow = hr_rows + warp * (32 * PITCH);          // this warp's row buffer
   float l_d = 0.f, l_c = 0.f, l_o = 0.f;              // every lane carries the same per-ray values; lane 0's are used
   float sb0 = 0.f, sb1 = 0.f, sb2 = 0.f, sb3 = 0.f;   // this lane's share of the head bias gradients
-  for (int ray = blockIdx.x * 4 + warp; ray < a.R; ray += gridDim.x * 4) {
-    const long long pb = (long long)ray * S, pi = pb + lane;
-    __syncwarp();                                     // the previous ray's rows are no longer read
+  auto stage_rows = [&](const __half* X, long long pb) {
 #pragma unroll 4
     for (int r0 = 0; r0 < S; r0 += RPP) {
       const int r = r0 + lane / LPR, cq = lane % LPR;
-      if (r < S) {
-        cp_async16(s4 + r * PITCH + cq * 16, X4 + (pb + r) * H + cq * 8);
-        cp_async16(sc + r * PITCH + cq * 16, XC + (pb + r) * H + cq * 8);
-      }
+      if (r < S) cp_async16(srow + r * PITCH + cq * 16, X + (pb + r) * H + cq * 8);
     }
     asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
     __syncwarp();
-    float oc = 0.f, zz = 0.f, c0 = 0.f, c1 = 0.f, c2 = 0.f;
+  };
+  const uint4* xrow = reinterpret_cast<const uint4*>(srow + lane * PITCH);
+  for (int ray = blockIdx.x * 4 + warp; ray < a.R; ray += gridDim.x * 4) {
+    const long long pb = (long long)ray * S, pi = pb + lane;
+    __syncwarp();                                     // the previous ray's rows are no longer read
+    stage_rows(X4, pb);
+    float ha = 0.f, h0 = 0.f, h1 = 0.f, h2 = 0.f;
     if (in) {
-      float ha = 0.f, h0 = 0.f, h1 = 0.f, h2 = 0.f;
-      const uint4* x4 = reinterpret_cast<const uint4*>(s4 + lane * PITCH);
-      const uint4* xc = reinterpret_cast<const uint4*>(sc + lane * PITCH);
+      float hb = 0.f;                                 // two chains: the dot product is FMA-latency bound otherwise
 #pragma unroll 4
       for (int q = 0; q < H / 8; ++q) {
-        const uint4 u = x4[q], v = xc[q];
+        const uint4 u = xrow[q];
         const __half* hu = reinterpret_cast<const __half*>(&u);
+#pragma unroll
+        for (int j = 0; j < 8; j += 2) {
+          ha = fmaf(__half2float(hu[j]), w[q * 8 + j], ha);
+          hb = fmaf(__half2float(hu[j + 1]), w[q * 8 + j + 1], hb);
+        }
+      }
+      ha += hb;
+    }
+    __syncwarp();
+    stage_rows(XC, pb);                               // hc stays staged for the backward half
+    float oc = 0.f, zz = 0.f, c0 = 0.f, c1 = 0.f, c2 = 0.f;
+    if (in) {
+#pragma unroll 4
+      for (int q = 0; q < H / 8; ++q) {
+        const uint4 v = xrow[q];
         const __half* hv = reinterpret_cast<const __half*>(&v);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const float f4 = __half2float(hu[j]), fc = __half2float(hv[j]);
+          const float fc = __half2float(hv[j]);
           const int o = q * 8 + j;
-          ha = fmaf(f4, w[o], ha);
           h0 = fmaf(fc, w[H + o], h0); h1 = fmaf(fc, w[2 * H + o], h1); h2 = fmaf(fc, w[3 * H + o], h2);
         }
       }
@@ -318,8 +331,7 @@ __global__ void __launch_bounds__(128) k_lw_heads_render(RenderArgs a, const __h
       __half2 h01 = __floats2half2_rn(fminf(fmaxf(LS * dh.x, -60000.f), 60000.f), fminf(fmaxf(LS * dh.y, -60000.f), 60000.f));
       __half2 h23 = __floats2half2_rn(fminf(fmaxf(LS * dh.z, -60000.f), 60000.f), fminf(fmaxf(LS * dh.w, -60000.f), 60000.f));
       reinterpret_cast<uint4*>(dh16)[pi] = make_uint4(*reinterpret_cast<uint32_t*>(&h01), *reinterpret_cast<uint32_t*>(&h23), 0u, 0u);
-      const uint4* xc = reinterpret_cast<const uint4*>(sc + lane * PITCH);   // second pass over the staged hc row
-      uint4* out = reinterpret_cast<uint4*>(dYc + pi * H);
+      uint4* xc = const_cast<uint4*>(xrow);             // second pass over the staged hc row, gated IN PLACE
       const float d0 = LS * dh.y, d1 = LS * dh.z, d2 = LS * dh.w;
 #pragma unroll 4
       for (int q = 0; q < H / 8; ++q) {
@@ -336,8 +348,15 @@ __global__ void __launch_bounds__(128) k_lw_heads_render(RenderArgs a, const __h
           __half2 hh = __floats2half2_rn(x0, x1);
           r[j] = *reinterpret_cast<uint32_t*>(&hh);
         }
-        out[q] = make_uint4(r[0], r[1], r[2], r[3]);
+        xc[q] = make_uint4(r[0], r[1], r[2], r[3]);
       }
+    }
+    __syncwarp();
+    // the ray's dYc rows leave as whole 2H-byte rows (the mirror image of the staging copies)
+#pragma unroll 4
+    for (int r0 = 0; r0 < S; r0 += RPP) {
+      const int r = r0 + lane / LPR, cq = lane % LPR;
+      if (r < S) *reinterpret_cast<uint4*>(dYc + (pb + r) * H + cq * 8) = *reinterpret_cast<const uint4*>(srow + r * PITCH + cq * 16);
     }
   }
   if (lane == 0) { atomicAdd(&s_loss[0], l_d); atomicAdd(&s_loss[1], l_c); atomicAdd(&s_loss[2], l_o); }
@@ -496,7 +515,7 @@ static int step_object(Workspace& ws, const VmbLayout& L, const StepParams& sp, 
       attr_set[dev & 63] = true;
     }
   }
-  const int hr_per_sm = std::max(1, std::min(8, (int)(220 * 1024 / (hr_smem<H>() + 8 * 1024))));
+  const int hr_per_sm = std::max(1, std::min(8, (int)(227 * 1024 / (hr_smem<H>() + 6 * 1024))));
   k_lw_heads_render<H><<<std::min((sp.R + 3) / 4, 148 * hr_per_sm), 128, hr_smem<H>(), st>>>(ra, ws.X4, ws.XC, Pb, L, ws.dYc, ws.dh16,
                                                                                           ws.dalpha_s, G);
   LW_TRY(cudaGetLastError());
