@@ -97,3 +97,22 @@ def test_sampler_tables_packing_round_trip():
     assert rd(a2.bbox, B, C.c_longlong).tolist() == [s.bbox.data_ptr() for s in sets]
     assert rd(a2.n_keyframes, B, C.c_int).tolist() == [5, 4, 3]
     assert rd(a2.latest_kf, 2 * B, C.c_int).tolist() == [3, 4, 2, 3, 1, 2]
+
+
+def test_synth_matches_oracle_generators():
+    """`vmap_b200/synth.py` exists so that bench.py's product arm never imports `oracle/`; it must stay the same
+    generator as the oracle's (same seeds -> same tensors), or the two bench arms would run different workloads."""
+    import torch
+    from oracle import vmap_oracle as vo
+    from vmap_b200 import synth
+    for kw in (dict(B=3, R=17, S=10, seed=5), dict(B=1, R=9, S=14, seed=6, n_cam2surf=5)):
+        a = vo.synthetic_batch(kw["B"], kw["R"], kw["S"], seed=kw["seed"], **({"n_cam2surf": kw["n_cam2surf"]} if "n_cam2surf" in kw else {}))
+        b = synth.synthetic_batch(kw["B"], kw["R"], kw["S"], seed=kw["seed"], **({"n_cam2surf": kw["n_cam2surf"]} if "n_cam2surf" in kw else {}))
+        assert a.keys() == b.keys()
+        for k in a:
+            assert torch.equal(torch.as_tensor(a[k]), torch.as_tensor(b[k])), k
+    for H in (32, 128):
+        pa, pb = vo.init_params(2, H, seed=11), synth.init_params(2, H, seed=11)
+        assert pa.keys() == pb.keys()
+        for k in pa:
+            assert torch.equal(torch.as_tensor(pa[k]), torch.as_tensor(pb[k])), k
