@@ -36,6 +36,29 @@ constexpr float LS = 256.0f, INV_LS = 1.0f / 256.0f;
 
 enum Epi { EPI_RELU_F16 = 0, EPI_GATE_F16 = 1, EPI_F32 = 2, EPI_ATOMIC = 3 };
 
+// Host side of programmatic dependent launch.  The orchestrator arms `t_pdl_next` right before a launch that directly
+// follows another kernel of the chain on the same stream; `launch_k` consumes it.  Every kernel of the layer-wise path
+// executes `ptx::pdl_wait()` before it touches anything its predecessor wrote, so an armed launch only overlaps its
+// prologue (and the launch latency itself) with the predecessor's tail.  VMB_NO_PDL=1 turns it off.
+static thread_local bool t_pdl_next = false;
+static bool pdl_enabled() {
+  static int on = -1;
+  if (on < 0) on = getenv("VMB_NO_PDL") == nullptr ? 1 : 0;
+  return on == 1;
+}
+static inline void pdl_arm() { t_pdl_next = pdl_enabled(); }
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = t_pdl_next ? 1 : 0;
+  t_pdl_next = false;
+  return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
+
 struct GemmArgs {
   int M, N;                 // valid output extent
   int K1, K2;               // K taken from A source 1 / source 2 (multiples of 16; K2 may be 0)
@@ -264,6 +287,8 @@ k_gemm_umma(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ C
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tm = *tmem_slot;
+  ptx::pdl_wait();                 // everything above overlapped the predecessor's tail (programmatic dependent launch)
+  ptx::pdl_launch_dependents();
 
 #define TILE_COORDS(T)                                                              \
   const int tz = (T) / (g.mt * g.nt), trem = (T) - tz * (g.mt * g.nt);              \
@@ -404,6 +429,8 @@ k_gemm_ws(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUt
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tm = *tmem_slot;
+  ptx::pdl_wait();                 // barrier init / TMEM alloc / bias staging (parameters: written launches ago) overlap the predecessor
+  ptx::pdl_launch_dependents();
 
   if (warp == 8) {
     // ===================== TMA producer: B once, then the A ring =====================
@@ -562,8 +589,7 @@ static cudaError_t launch_gemm(const Operand& a1, const Operand& a2, const Opera
   g.mt = m_tiles; g.nt = n_tiles; g.zt = z;
   const long long total = (long long)m_tiles * n_tiles * z;
   const int grid = (int)std::min<long long>(total, 2LL * n_sm[dev & 63]);
-  k_gemm_umma<A_MN, B_MN, EPI><<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(mA1, mA2, mB, g);
-  return cudaGetLastError();
+  return launch_k(k_gemm_umma<A_MN, B_MN, EPI>, dim3(grid), dim3(GEMM_THREADS), GEMM_SMEM, st, mA1, mA2, mB, g);
 }
 
 // Weight-stationary launch (A K-major, single N tile).  Returns cudaErrorNotSupported when the shape does not fit
@@ -600,8 +626,7 @@ static cudaError_t launch_gemm_ws(const Operand& a1, const Operand& a2, const Op
   if (!n_sm[dev & 63]) cudaDeviceGetAttribute(&n_sm[dev & 63], cudaDevAttrMultiProcessorCount, dev);
   g.mt = m_tiles; g.nt = 1; g.zt = 1;
   const int grid = std::min(m_tiles, n_sm[dev & 63]);
-  k_gemm_ws<B_MN, EPI><<<grid, WS_THREADS, WS_SMEM, st>>>(mA1, mA2, mB, mB2, g, geo);
-  return cudaGetLastError();
+  return launch_k(k_gemm_ws<B_MN, EPI>, dim3(grid), dim3(WS_THREADS), WS_SMEM, st, mA1, mA2, mB, mB2, g, geo);
 }
 
 // forward / dgrad GEMMs: weight-stationary when the shape fits, generic otherwise

@@ -119,6 +119,8 @@ __device__ __forceinline__ void sincos_ladder6(float proj, float (&s)[6], float 
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) k_lw_pe(const float* __restrict__ pcs, const float* __restrict__ dirs,
                                                const float* __restrict__ scale_ptr, long long P, __half* __restrict__ E) {
+  ptx::pdl_wait();
+  ptx::pdl_launch_dependents();
   const float scale = *scale_ptr;
   __shared__ __align__(16) __half row[128 * EW];
   const long long p0 = (long long)blockIdx.x * 128, p = p0 + threadIdx.x;
@@ -153,6 +155,8 @@ template <int H>
 __global__ void __launch_bounds__(128) k_lw_heads(const __half* __restrict__ X4, const __half* __restrict__ XC,
                                                   const float* __restrict__ P, VmbLayout L, long long np,
                                                   float* __restrict__ occ, float* __restrict__ col, int raw) {
+  ptx::pdl_wait();
+  ptx::pdl_launch_dependents();
   // raw != 0 (eval_points, trainer.py:77-90): occ receives alpha*10 before the sigmoid
   __shared__ float w[4 * H];
   for (int i = threadIdx.x; i < H; i += 128) w[i] = P[L.o_Wa + i];
@@ -212,6 +216,8 @@ __global__ void __launch_bounds__(128) k_lw_heads_render(RenderArgs a, const __h
                                                          const float* __restrict__ P, VmbLayout L, __half* __restrict__ dYc,
                                                          __half* __restrict__ dh16, float* __restrict__ dalpha_s,
                                                          float* __restrict__ G) {
+  ptx::pdl_wait();
+  ptx::pdl_launch_dependents();
   extern __shared__ __align__(16) unsigned char hr_rows[];
   __shared__ float w[4 * H];                          // [0,H) out_alpha row, [H,4H) out_color rows
   __shared__ int s_on[3];
@@ -375,6 +381,8 @@ __global__ void __launch_bounds__(128) k_lw_heads_render(RenderArgs a, const __h
 
 // column sums of a [P][H] fp16 gradient block -> bias gradient (x 2^-8); `rows` rows per block
 __global__ void __launch_bounds__(256) k_lw_colsum(const __half* __restrict__ dY, long long np, int H, int rows, float* __restrict__ gb) {
+  ptx::pdl_wait();
+  ptx::pdl_launch_dependents();
   const int c = threadIdx.x;
   if (c >= H) return;
   const long long r0 = (long long)blockIdx.x * rows, r1 = min(np, r0 + rows);
@@ -396,6 +404,8 @@ constexpr int PEB_SMEM = 128 * PEB_LD * 4;
 __global__ void __launch_bounds__(128) k_lw_pe_bwd(const float* __restrict__ pcs, const float* __restrict__ dirs,
                                                    const float* __restrict__ scale_ptr, long long P,
                                                    const float* __restrict__ dE, float* __restrict__ gB) {
+  ptx::pdl_wait();
+  ptx::pdl_launch_dependents();
   extern __shared__ float sg[];                 // [128 points][PEB_LD]: the dE rows of this block, staged coalesced
   const float scale = *scale_ptr;
   __shared__ float st[3][129];
@@ -483,10 +493,11 @@ static int step_object(Workspace& ws, const VmbLayout& L, const StepParams& sp, 
   const Operand opE1{ws.E, np, E1W, EW}, opE2{ws.E + E1W, np, E2W, EW};
 
   // ---- forward ----
-  k_lw_pe<<<nblk, 128, 0, st>>>(pcs, dirs, scale_p, np, ws.E);
+  LW_TRY(launch_k(k_lw_pe, dim3(nblk), dim3(128), 0, st, pcs, dirs, scale_p, np, ws.E));
   auto fwd = [&](const Operand& a1, const Operand& a2, int K1, int K2, long long woff, int ldw, int boff, __half* out) {
     GemmArgs g; memset(&g, 0, sizeof(g));
     g.M = (int)np; g.N = H; g.K1 = K1; g.K2 = K2; g.bias = Pb + boff; g.out16 = out; g.ldo = H; g.scale = 1.0f;
+    pdl_arm();                                          // follows k_lw_pe / the previous layer directly on `st`
     return launch_gemm_auto<0, EPI_RELU_F16>(a1, a2, Operand{Wi + woff, H, ldw, ldw}, g, mt, (H + BN - 1) / BN, st);
   };
   LW_TRY(fwd(opE1, none, E1W, 0, 0, 96, L.o_bin, ws.X1));
@@ -495,9 +506,9 @@ static int step_object(Workspace& ws, const VmbLayout& L, const StepParams& sp, 
   LW_TRY(fwd(opX(ws.X3), none, H, 0, off_m2(H), H, L.o_bm2, ws.X4));
   LW_TRY(fwd(opX(ws.X4), opE2, H, E2W, off_cl(H), H + 48, L.o_bcl, ws.XC));
   if (sp.fwd_only) {
-    k_lw_heads<H><<<nblk, 128, 0, st>>>(ws.X4, ws.XC, Pb, L, np, sp.out_alpha + (size_t)b * sp.alpha_stride + fwd_p0,
-                                        sp.out_colour + (size_t)b * sp.colour_stride + fwd_p0 * 3, 1);
-    LW_TRY(cudaGetLastError());
+    pdl_arm();
+    LW_TRY(launch_k(k_lw_heads<H>, dim3(nblk), dim3(128), 0, st, (const __half*)ws.X4, (const __half*)ws.XC, Pb, L, np,
+                    sp.out_alpha + (size_t)b * sp.alpha_stride + fwd_p0, sp.out_colour + (size_t)b * sp.colour_stride + fwd_p0 * 3, 1));
     return 0;
   }
   RenderArgs ra;
@@ -516,9 +527,9 @@ static int step_object(Workspace& ws, const VmbLayout& L, const StepParams& sp, 
     }
   }
   const int hr_per_sm = std::max(1, std::min(8, (int)(227 * 1024 / (hr_smem<H>() + 6 * 1024))));
-  k_lw_heads_render<H><<<std::min((sp.R + 3) / 4, 148 * hr_per_sm), 128, hr_smem<H>(), st>>>(ra, ws.X4, ws.XC, Pb, L, ws.dYc, ws.dh16,
-                                                                                          ws.dalpha_s, G);
-  LW_TRY(cudaGetLastError());
+  pdl_arm();
+  LW_TRY(launch_k(k_lw_heads_render<H>, dim3(std::min((sp.R + 3) / 4, 148 * hr_per_sm)), dim3(128), (size_t)hr_smem<H>(), st, ra,
+                  (const __half*)ws.X4, (const __half*)ws.XC, Pb, L, ws.dYc, ws.dh16, ws.dalpha_s, G));
   if (!sp.backward) return 0;
 
   // ---- backward ----
@@ -557,29 +568,36 @@ static int step_object(Workspace& ws, const VmbLayout& L, const StepParams& sp, 
     LW_TRY(fork(0));                                    // dYc (= d colour hidden), dh16 ready: heads + color_linear wgrads on the side stream
     LW_TRY((launch_gemm<1, 1, EPI_ATOMIC>(Operand{ws.X4, np, H, H}, none, Operand{ws.dh16, np, 8, 8}, g, (H + BM - 1) / BM, 1, zs, sd)));
     g.gdst = G + L.o_Woc - H; g.ldgn = H; g.n_lo = 1; g.n_valid = 4;
+    pdl_arm();
     LW_TRY((launch_gemm<1, 1, EPI_ATOMIC>(Operand{ws.XC, np, H, H}, none, Operand{ws.dh16, np, 8, 8}, g, (H + BM - 1) / BM, 1, zs, sd)));
   }
   // color_linear
+  pdl_arm();
   LW_TRY(wgrad(ws.dYc, opX(ws.X4), H, L.o_Wcl, H + L.e2, H, -1, -1));
+  pdl_arm();
   LW_TRY(wgrad(ws.dYc, opE2, E2W, L.o_Wcl + H, H + L.e2, L.e2, ONES2, L.o_bcl));
-  LW_TRY(dgrad_emb(ws.dYc, off_cl(H) + H, H + 48, E2W, E1W, 0));
+  LW_TRY(dgrad_emb(ws.dYc, off_cl(H) + H, H + 48, E2W, E1W, 0));                // first kernel on `st` after the fork: not armed
+  pdl_arm();
   LW_TRY(dgrad_gate(ws.dYc, off_cl(H), H + 48, ws.X4, ws.dYa, ws.dalpha_s, Pb + L.o_Wa));          // dY4 -> dYa
   // mid2
   LW_TRY(fork(1));
   LW_TRY(wgrad(ws.dYa, opX(ws.X3), H, L.o_Wm2, H, H, -1, -1));
-  k_lw_colsum<<<(int)((np + cs_rows - 1) / cs_rows), 256, 0, sd>>>(ws.dYa, np, H, cs_rows, G + L.o_bm2);
+  pdl_arm();                                          // follows this layer's weight-gradient GEMM directly on the side stream
+  LW_TRY(launch_k(k_lw_colsum, dim3((unsigned)((np + cs_rows - 1) / cs_rows)), dim3(256), 0, sd, (const __half*)ws.dYa, np, H, cs_rows, G + L.o_bm2));
   LW_TRY(cudaEventRecord(ws.ev_side[0], sd));           // the side stream is done reading dYc (dY of color_linear) and dYa (dY4)
   LW_TRY(dgrad_gate(ws.dYa, off_m2(H), H, ws.X3, ws.dYb, nullptr, nullptr));                        // dY3 -> dYb
   // cat_layer
   LW_TRY(fork(2));
   LW_TRY(wgrad(ws.dYb, opX(ws.X2), H, L.o_Wcat, H + VMB_E1, H, -1, -1));
+  pdl_arm();
   LW_TRY(wgrad(ws.dYb, opE1, E1W, L.o_Wcat + H, H + VMB_E1, VMB_E1, ONES1, L.o_bcat));
   LW_TRY(cudaStreamWaitEvent(st, ws.ev_side[0], 0));    // dYa / dYc are about to be overwritten
   LW_TRY(dgrad_gate(ws.dYb, off_cat(H), H + 96, ws.X2, ws.dYa, nullptr, nullptr));                  // dY2 -> dYa (dY3 stays in dYb)
   // mid1
   LW_TRY(fork(3));
   LW_TRY(wgrad(ws.dYa, opX(ws.X1), H, L.o_Wm1, H, H, -1, -1));
-  k_lw_colsum<<<(int)((np + cs_rows - 1) / cs_rows), 256, 0, sd>>>(ws.dYa, np, H, cs_rows, G + L.o_bm1);
+  pdl_arm();                                          // follows this layer's weight-gradient GEMM directly on the side stream
+  LW_TRY(launch_k(k_lw_colsum, dim3((unsigned)((np + cs_rows - 1) / cs_rows)), dim3(256), 0, sd, (const __half*)ws.dYa, np, H, cs_rows, G + L.o_bm1));
   LW_TRY(dgrad_gate(ws.dYa, off_m1(H), H, ws.X1, ws.dYc, nullptr, nullptr));                        // dY1 -> dYc (free since color_linear)
   // in_layer
   LW_TRY(fork(4));
@@ -605,7 +623,8 @@ static int step_object(Workspace& ws, const VmbLayout& L, const StepParams& sp, 
       attr_set[dev & 63] = true;
     }
   }
-  k_lw_pe_bwd<<<nblk, 128, PEB_SMEM, st>>>(pcs, dirs, scale_p, np, ws.dE, G + L.o_B);
+  pdl_arm();                                          // follows the embedding-gradient GEMM directly on `st`
+  LW_TRY(launch_k(k_lw_pe_bwd, dim3(nblk), dim3(128), (size_t)PEB_SMEM, st, pcs, dirs, scale_p, np, (const float*)ws.dE, G + L.o_B));
   LW_TRY(cudaStreamWaitEvent(st, ws.ev_side[1], 0));    // join: every weight-gradient GEMM of this object has been enqueued before what follows
   LW_TRY(cudaGetLastError());
   return 0;

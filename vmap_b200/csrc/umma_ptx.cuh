@@ -5,6 +5,12 @@
 #include <stdint.h>
 
 namespace ptx {
+// Programmatic dependent launch: a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start
+// while its predecessor on the stream is still running; `pdl_wait` blocks until that predecessor has completed and its
+// writes are visible (a no-op for an ordinary launch), `pdl_launch_dependents` lets the successor be scheduled early.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
