@@ -489,6 +489,11 @@ static int step_object(Workspace& ws, const VmbLayout& L, const StepParams& sp, 
   const float* scale_p = sp.scale + b;
   const int nblk = (int)((np + 127) / 128);
   const Operand none{nullptr, 0, 0, 0};
+  // programmatic dependent launch pays where the step is a chain of short single-wave kernels (background model, iMAP
+  // shards: -3..5 %); at the full iMAP shape the kernels are HBM-bound for tens of microseconds and the early launch of
+  // the successor only takes resources from them (+1 %): armed below 64 K points only
+  const bool pdl_ok = np <= 65536;
+  auto arm = [&]() { if (pdl_ok) pdl_arm(); };
   auto opX = [&](const __half* x) { return Operand{x, np, H, H}; };
   const Operand opE1{ws.E, np, E1W, EW}, opE2{ws.E + E1W, np, E2W, EW};
 
@@ -497,7 +502,7 @@ static int step_object(Workspace& ws, const VmbLayout& L, const StepParams& sp, 
   auto fwd = [&](const Operand& a1, const Operand& a2, int K1, int K2, long long woff, int ldw, int boff, __half* out) {
     GemmArgs g; memset(&g, 0, sizeof(g));
     g.M = (int)np; g.N = H; g.K1 = K1; g.K2 = K2; g.bias = Pb + boff; g.out16 = out; g.ldo = H; g.scale = 1.0f;
-    pdl_arm();                                          // follows k_lw_pe / the previous layer directly on `st`
+    arm();                                          // follows k_lw_pe / the previous layer directly on `st`
     return launch_gemm_auto<0, EPI_RELU_F16>(a1, a2, Operand{Wi + woff, H, ldw, ldw}, g, mt, (H + BN - 1) / BN, st);
   };
   LW_TRY(fwd(opE1, none, E1W, 0, 0, 96, L.o_bin, ws.X1));
@@ -506,7 +511,7 @@ static int step_object(Workspace& ws, const VmbLayout& L, const StepParams& sp, 
   LW_TRY(fwd(opX(ws.X3), none, H, 0, off_m2(H), H, L.o_bm2, ws.X4));
   LW_TRY(fwd(opX(ws.X4), opE2, H, E2W, off_cl(H), H + 48, L.o_bcl, ws.XC));
   if (sp.fwd_only) {
-    pdl_arm();
+    arm();
     LW_TRY(launch_k(k_lw_heads<H>, dim3(nblk), dim3(128), 0, st, (const __half*)ws.X4, (const __half*)ws.XC, Pb, L, np,
                     sp.out_alpha + (size_t)b * sp.alpha_stride + fwd_p0, sp.out_colour + (size_t)b * sp.colour_stride + fwd_p0 * 3, 1));
     return 0;
@@ -527,7 +532,7 @@ static int step_object(Workspace& ws, const VmbLayout& L, const StepParams& sp, 
     }
   }
   const int hr_per_sm = std::max(1, std::min(8, (int)(227 * 1024 / (hr_smem<H>() + 6 * 1024))));
-  pdl_arm();
+  arm();
   LW_TRY(launch_k(k_lw_heads_render<H>, dim3(std::min((sp.R + 3) / 4, 148 * hr_per_sm)), dim3(128), (size_t)hr_smem<H>(), st, ra,
                   (const __half*)ws.X4, (const __half*)ws.XC, Pb, L, ws.dYc, ws.dh16, ws.dalpha_s, G));
   if (!sp.backward) return 0;
@@ -568,35 +573,35 @@ static int step_object(Workspace& ws, const VmbLayout& L, const StepParams& sp, 
     LW_TRY(fork(0));                                    // dYc (= d colour hidden), dh16 ready: heads + color_linear wgrads on the side stream
     LW_TRY((launch_gemm<1, 1, EPI_ATOMIC>(Operand{ws.X4, np, H, H}, none, Operand{ws.dh16, np, 8, 8}, g, (H + BM - 1) / BM, 1, zs, sd)));
     g.gdst = G + L.o_Woc - H; g.ldgn = H; g.n_lo = 1; g.n_valid = 4;
-    pdl_arm();
+    arm();
     LW_TRY((launch_gemm<1, 1, EPI_ATOMIC>(Operand{ws.XC, np, H, H}, none, Operand{ws.dh16, np, 8, 8}, g, (H + BM - 1) / BM, 1, zs, sd)));
   }
   // color_linear
-  pdl_arm();
+  arm();
   LW_TRY(wgrad(ws.dYc, opX(ws.X4), H, L.o_Wcl, H + L.e2, H, -1, -1));
-  pdl_arm();
+  arm();
   LW_TRY(wgrad(ws.dYc, opE2, E2W, L.o_Wcl + H, H + L.e2, L.e2, ONES2, L.o_bcl));
   LW_TRY(dgrad_emb(ws.dYc, off_cl(H) + H, H + 48, E2W, E1W, 0));                // first kernel on `st` after the fork: not armed
-  pdl_arm();
+  arm();
   LW_TRY(dgrad_gate(ws.dYc, off_cl(H), H + 48, ws.X4, ws.dYa, ws.dalpha_s, Pb + L.o_Wa));          // dY4 -> dYa
   // mid2
   LW_TRY(fork(1));
   LW_TRY(wgrad(ws.dYa, opX(ws.X3), H, L.o_Wm2, H, H, -1, -1));
-  pdl_arm();                                          // follows this layer's weight-gradient GEMM directly on the side stream
+  arm();                                          // follows this layer's weight-gradient GEMM directly on the side stream
   LW_TRY(launch_k(k_lw_colsum, dim3((unsigned)((np + cs_rows - 1) / cs_rows)), dim3(256), 0, sd, (const __half*)ws.dYa, np, H, cs_rows, G + L.o_bm2));
   LW_TRY(cudaEventRecord(ws.ev_side[0], sd));           // the side stream is done reading dYc (dY of color_linear) and dYa (dY4)
   LW_TRY(dgrad_gate(ws.dYa, off_m2(H), H, ws.X3, ws.dYb, nullptr, nullptr));                        // dY3 -> dYb
   // cat_layer
   LW_TRY(fork(2));
   LW_TRY(wgrad(ws.dYb, opX(ws.X2), H, L.o_Wcat, H + VMB_E1, H, -1, -1));
-  pdl_arm();
+  arm();
   LW_TRY(wgrad(ws.dYb, opE1, E1W, L.o_Wcat + H, H + VMB_E1, VMB_E1, ONES1, L.o_bcat));
   LW_TRY(cudaStreamWaitEvent(st, ws.ev_side[0], 0));    // dYa / dYc are about to be overwritten
   LW_TRY(dgrad_gate(ws.dYb, off_cat(H), H + 96, ws.X2, ws.dYa, nullptr, nullptr));                  // dY2 -> dYa (dY3 stays in dYb)
   // mid1
   LW_TRY(fork(3));
   LW_TRY(wgrad(ws.dYa, opX(ws.X1), H, L.o_Wm1, H, H, -1, -1));
-  pdl_arm();                                          // follows this layer's weight-gradient GEMM directly on the side stream
+  arm();                                          // follows this layer's weight-gradient GEMM directly on the side stream
   LW_TRY(launch_k(k_lw_colsum, dim3((unsigned)((np + cs_rows - 1) / cs_rows)), dim3(256), 0, sd, (const __half*)ws.dYa, np, H, cs_rows, G + L.o_bm1));
   LW_TRY(dgrad_gate(ws.dYa, off_m1(H), H, ws.X1, ws.dYc, nullptr, nullptr));                        // dY1 -> dYc (free since color_linear)
   // in_layer
@@ -623,7 +628,7 @@ static int step_object(Workspace& ws, const VmbLayout& L, const StepParams& sp, 
       attr_set[dev & 63] = true;
     }
   }
-  pdl_arm();                                          // follows the embedding-gradient GEMM directly on `st`
+  arm();                                          // follows the embedding-gradient GEMM directly on `st`
   LW_TRY(launch_k(k_lw_pe_bwd, dim3(nblk), dim3(128), (size_t)PEB_SMEM, st, pcs, dirs, scale_p, np, (const float*)ws.dE, G + L.o_B));
   LW_TRY(cudaStreamWaitEvent(st, ws.ev_side[1], 0));    // join: every weight-gradient GEMM of this object has been enqueued before what follows
   LW_TRY(cudaGetLastError());
