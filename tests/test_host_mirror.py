@@ -116,3 +116,17 @@ def test_synth_matches_oracle_generators():
         assert pa.keys() == pb.keys()
         for k in pa:
             assert torch.equal(torch.as_tensor(pa[k]), torch.as_tensor(pb[k])), k
+
+
+def test_rows_dense_equals_per_object_contiguity():
+    """`ensemble.rows_dense(t)` must say exactly what `t[0].is_contiguous()` says (it replaces that check on the
+    per-step path without building six views per call)."""
+    import itertools
+    import torch
+    from vmap_b200.ensemble import rows_dense
+    base = torch.zeros(4, 12, 5, 3)
+    views = [base, base[:, 2:7], base[:, ::2], base[:, :, 1:3], base[..., 0], base[:, :, :, :2], base[1:2], base[:, 3:4],
+             base.permute(0, 2, 1, 3), base[:, :, 2], torch.zeros(3, 7)[:, 1:5], torch.zeros(3, 7).t(), torch.zeros(2, 1, 6)[:, :, ::2],
+             torch.zeros(5, 8, dtype=torch.uint8)[:, 2:6], base.expand(4, 12, 5, 3), torch.zeros(1, 9, 3).expand(4, 9, 3)]
+    for v in views:
+        assert rows_dense(v) == v[0].is_contiguous(), (tuple(v.shape), v.stride())
